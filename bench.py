@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- questions/sec of the GNN retrieval hot path (ReaRev forward + score + candidate ranking) on
+WebQSP-shape synthetic subgraphs, with the aggregation kernel's achieved HBM bandwidth (roofline) and the
+CPU oracle port timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch: CSR batching of the fact list -> TypeLayer ->
+num_iter x num_gnn GNN layers (aggregation + e2e linear + score/softmax) -> instruction updates -> loss ->
+candidate ranking.  `value` times steps whose inputs (raw fact arrays etc.) are already in HBM, with CUDA
+events on the launching stream (L2 flushed between steps); `e2e` times model.forward(host batch) + retrieve:
+pinned-host -> device copies, CSR batching, forward, ranking and the device -> host read of the retrieved
+candidate lists, by wall clock between synchronizes.  Multi-GPU: one process per GPU, every rank runs its
+own B questions (weak scaling), no communication during the forward, one NCCL all-gather of the answer
+scores at the end of each step; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gnn_rag_b200 import synthetic as S  # noqa: E402
+
+METRIC = "questions/sec (GNN forward+score) on WebQSP-shape subgraphs; agg-kernel HBM GB/s"
+UNIT = "questions/s"
+WORKLOADS = {
+    "cfg1": "single WebQSP question, ~2k-node/~6k-edge subgraph, 3-hop ReaRev fp32",
+    "cfg2": "batch=64 WebQSP-shape synthetic subgraphs (~2k nodes, 200-dim feat, 3 hops) on 1xB200",
+    "cfg3": "batch=256 CWQ-shape synthetic subgraphs (~10k nodes, ~40k edges, 4 hops)",
+    "cfg5": "stress: 100k-node / 1M-edge synthetic subgraph, 400-dim feat, 3 hops",
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=8, help="questions in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--agg-tma", type=int, default=None)
+    return ap.parse_args()
+
+
+def model_args_for(c, use_cuda):
+    return S.model_args("ReaRev", entity_dim=c["D"], num_iter=c["T"], num_ins=c["I"], num_gnn=c["K"],
+                        use_cuda=use_cuda)
+
+
+def make_cfg_batch(c, seed, B=None):
+    B = c["B"] if B is None else B
+    return S.make_batch(seed, B=B, N=c["N"], E=c["E"], with_weights=False)
+
+
+def config_dict(name, c, extra=None):
+    d = {"workload": "%s: %s" % (name, WORKLOADS[name]), "questions_per_gpu": c["B"], "nodes": c["N"],
+         "kg_edges": c["E"], "facts_incl_self_loops": c["E"] + c["N"], "feat_dim": c["D"],
+         "num_iter": c["T"], "num_gnn": c["K"], "num_ins": c["I"],
+         "relations": S.WEBQSP_NUM_RELATION, "seeds": {"data": 1, "weights": 0}}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU oracle port (cpu_baseline / --impl reference)
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_run(c, sd_cpu, nq, steps, warmup):
+    """Time the oracle port (oracle/kgqa_oracle.py: the reference's op sequence on torch-CPU) on `nq`
+    questions of the workload with all host threads.  Returns (questions/s, ms/step, cores)."""
+    from oracle import kgqa_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args = model_args_for(c, False)
+    batch = make_cfg_batch(c, 1, B=nq)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            _, _, dist = O.forward(sd_cpu, args, S.WEBQSP_NUM_ENTITY, S.WEBQSP_NUM_WORD, batch)
+            O.rank_candidates(batch[0], batch[1], dist.numpy(), S.WEBQSP_NUM_ENTITY, args["eps"])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    tot = sum(times)
+    return nq * len(times) / tot, 1e3 * tot / len(times), cores
+
+
+def init_state_dict_cpu(c):
+    """Random-init weights of the ReaRev architecture (torch.manual_seed(0)), CPU fp32."""
+    import gnn_rag_b200 as G
+    torch.manual_seed(0)
+    m = G.ReaRev(model_args_for(c, False), S.WEBQSP_NUM_ENTITY, S.WEBQSP_NUM_RELATION, S.WEBQSP_NUM_WORD)
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c = S.CONFIGS[a.config]
+    sd = init_state_dict_cpu(c)
+    nq = min(a.cpu_sample, c["B"])
+    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
+    qps, ms, cores = cpu_oracle_run(c, sd, nq, steps, warmup)
+    sample = "%d of %d questions per step, %d timed steps" % (nq, c["B"], steps)
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(a.config, c),
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def agg_algorithmic_bytes(B, N, F, D, I, R1):
+    """Minimal HBM bytes of ONE fused aggregation launch (both directions, I instructions), fp32/int32:
+    two CSRs (src+rel per edge, row pointers), prior, two relation tables, instructions, 2*I output rows.
+    (= 2*I units of SURVEY.md 8d minus the reads the fused launch shares.)"""
+    Nt = B * N
+    return 2 * F * 8 + 2 * (Nt + 1) * 4 + Nt * 4 + 2 * R1 * D * 4 + B * I * D * 4 + 2 * I * Nt * D * 4
+
+
+def run_ours(a):
+    import torch.distributed as dist
+
+    import gnn_rag_b200 as G
+    from gnn_rag_b200 import batching, evaluate, ops, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if a.agg_tma is not None:
+        ops.set_option("agg_tma", a.agg_tma)
+    c = S.CONFIGS[a.config]
+    B, N, D, I = c["B"], c["N"], c["D"], c["I"]
+    args = model_args_for(c, True)
+    torch.manual_seed(0)
+    model = G.ReaRev(dict(args), S.WEBQSP_NUM_ENTITY, S.WEBQSP_NUM_RELATION, S.WEBQSP_NUM_WORD).eval()
+    R1 = S.WEBQSP_NUM_RELATION + 1
+    host_batch = make_cfg_batch(c, 1 + rank)
+    F = len(host_batch[2][0])
+    pinned = batching.pin_batch(host_batch)
+    # device-resident raw inputs for the `value` leg (fact arrays stay int64 exactly as the loader emits)
+    dev_batch = tuple(
+        (tuple(x.to(dev) if isinstance(x, torch.Tensor) else x for x in t) if isinstance(t, tuple)
+         else (t.to(dev) if isinstance(t, torch.Tensor) else t)) for t in pinned)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    eps = args["eps"]
+
+    def step(batch):
+        _loss, _pred, pred_dist, _ = model(batch)
+        cand = ops.rank_candidates(pred_dist, model.last_batch.local_entity,
+                                   model.last_batch.query_entities, S.WEBQSP_NUM_ENTITY, eps)
+        if world > 1:
+            parallel.all_gather_scores(pred_dist, B * world)
+        return pred_dist, cand
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        step(dev_batch)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: K steps, device-resident inputs, CUDA events, L2 flushed between steps -------
+    ops.STATS.reset()
+    ops.STATS.time_agg = True
+    evs = []
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(dev_batch)
+        e.record()
+        evs.append((s, e))
+    barrier()
+    wall = time.perf_counter() - wall0
+    ops.STATS.time_agg = False
+    launches = ops.STATS.launches
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    agg = [(s.elapsed_time(e), tag) for s, e, tag in ops.STATS.agg_events]
+    # ---- e2e: host (pinned) batch in, retrieved candidate lists out -------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(a.steps):
+        _loss, _pred, pred_dist, _ = model(pinned)
+        retrieved, nb = evaluate.retrieve(pred_dist, model.last_batch, S.WEBQSP_NUM_ENTITY, eps)
+        if world > 1:
+            parallel.all_gather_scores(pred_dist, B * world)
+        h2d, d2h = model.last_batch.h2d_bytes, nb
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- max over ranks ------------------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * B * a.steps / (dev_ms / 1e3)
+    e2e_value = world * B * a.steps / (e2e_ms / 1e3)
+    # ---- roofline of the dominant kernel (aggregation) ------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    per_step = len(agg) // max(a.steps, 1)
+    # layer 0 of every iteration sees the one-hot seed prior: almost every edge is skipped exactly
+    # (c_e == 0), so those launches are pure output writes; report dense-prior launches as the headline
+    K = c["K"]
+    dense = [ms for i, (ms, _) in enumerate(agg) if (i % per_step) % K != 0] if per_step else []
+    seedl = [ms for i, (ms, _) in enumerate(agg) if (i % per_step) % K == 0] if per_step else []
+    abytes = agg_algorithmic_bytes(B, N, F, D, I, R1)
+    dense_ms = float(np.mean(dense)) if dense else float("nan")
+    achieved = abytes / (dense_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "agg_kernel (gr_aggregate_dual)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dense_ms,
+                "launches_per_step": per_step,
+                "seed_prior_launch_ms": float(np.mean(seedl)) if seedl else None,
+                "agg_share_of_step": (sum(ms for ms, _ in agg) / dev_ms) if dev_ms else None}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(a.config, c, {
+                "global_questions": world * B, "l2": "256 MiB flush write between timed steps",
+                "timing": "CUDA events per step on the launch stream, max over ranks",
+                "wall_s_timed_region_incl_flush": wall}),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if not a.no_cpu_baseline and world == 1:
+        sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        nq = min(a.cpu_sample, B)
+        qps, ms, cores = cpu_oracle_run(c, sd_cpu, nq, 3, 1)
+        line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d of %d questions per forward, 3 timed forwards (oracle port of "
+                                          "the reference op sequence, torch-CPU, all host threads)" % (nq, B)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,420 @@
+// The aggregation kernel family: relation-typed neighbour aggregation over the destination-CSR subgraph.
+//
+// Replaces (reference paths): ReasonGNNLayer.reason_layer / reason_layer_inv
+// (gnn/modules/kg_reasoning/reasongnn.py:61-116), NSMLayer.reason_layer (nsm_gnn.py:87-112) and the
+// SpMM half of TypeLayer.forward (gnn/modules/layer_init.py:46-57).
+//
+// Math.  The reference computes, per fact f with relation r_f, question b_f and destination n,
+//     msg_f = relu( (W_k rel[r_f] + b_k) * ins[b_f] ) * w_f * (w_f * p[src_f])      and  out[n] = sum_f msg_f.
+// (W_k rel + b_k) only depends on the relation: it is hoisted to a table P[R1, D] (gr_linear).  With
+// c_f = w_f*(w_f*p[src_f]) >= 0 and, per element,  relu(P*x) = x*relu(P) for x >= 0 and (-x)*relu(-P) for
+// x < 0, the edge loop only needs two instruction-INDEPENDENT accumulators
+//     A[n] = sum_f c_f relu(P[r_f]),   Bn[n] = sum_f c_f relu(-P[r_f]),
+// and every instruction j is an epilogue  out_j[n] = x_j >= 0 ? x_j*A : (-x_j)*Bn.  The inner loop is
+// therefore 2 FMNMX + 2 FFMA per element per edge for any number of instructions.
+//
+// Work decomposition.  One CTA = one tile of kRows consecutive destination rows.  Phase 1 stages the
+// tile's row pointers and its contiguous edge slice (relation id + coefficient c_f, which needs the
+// prior gather) into shared memory, either with plain coalesced loads or with 1-D bulk TMA copies
+// (cp.async.bulk + mbarrier) of the raw src/rel slices.  Phase 2: one warp per row, lanes across the
+// feature dimension (128-bit loads of the L2-resident table row, 128-bit stores of the output row).
+// Reduction order inside a row = CSR slot order = original fact order: deterministic, atomic-free.
+//
+// Roofline: HBM-bound on the OUTPUT rows: per (direction, instruction) unit
+//   F*8 + (Nt+1)*4 + Nt*4 + R1*D*4 + B*D*4 + Nt*D*4 bytes.
+#include "common.cuh"
+
+namespace gr {
+
+int g_opt_agg_tma = 0;   // set through gr_set_option("agg_tma", 0|1)
+
+namespace {
+
+constexpr int kRows = 32;        // destination rows per CTA tile
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kEdgeCap = 512;    // staged edges per direction per tile; the rest takes the slow path
+
+enum { MODE_MSG = 0, MODE_TYPE = 1 };
+
+struct AggDir {
+  const int32_t* rowptr;
+  const int32_t* src;
+  const int32_t* rel;
+  const float* w;
+  const float* table;
+};
+
+struct AggParams {
+  AggDir dir[2];
+  int ndir;
+  const float* prior;
+  const float* ins;     // [B, I, D]
+  float* out;
+  float* possible;
+  int64_t out_row_stride, out_col0, seg_stride_j, seg_stride_dir;
+  int B, N, D, I, j0;   // this launch handles instructions j0 .. j0+NI-1
+  int64_t Nt, Fpad;
+};
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> { using T = float4; };
+template <> struct Vec<2> { using T = float2; };
+template <> struct Vec<1> { using T = float; };
+
+template <int VEC>
+__device__ __forceinline__ void ldg_vec(float (&v)[VEC], const float* p) {
+  using T = typename Vec<VEC>::T;
+  T t = __ldg(reinterpret_cast<const T*>(p));
+  const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = f[i];
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
+  using T = typename Vec<VEC>::T;
+  T t;
+  float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) f[i] = v[i];
+  *reinterpret_cast<T*>(p) = t;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// coefficient of one edge: c = w*(w*prior[src]) (reasongnn.py:80-84 applies the COO value twice when
+// normalized_gnn is on); TypeLayer: c = w (layer_init.py:39-42,52-53)
+template <int MODE>
+__device__ __forceinline__ float edge_coeff(const AggParams& p, const AggDir& d, int64_t e, int s) {
+  float w = d.w ? d.w[e] : 1.0f;
+  if (MODE == MODE_TYPE) return w;
+  float pr = p.prior[s];
+  return w * (w * pr);
+}
+
+template <int VEC, int NI, int MODE, bool USE_TMA>
+__global__ void __launch_bounds__(kThreads, 3) agg_kernel(const AggParams p) {
+  __shared__ int32_t s_rowptr[2][kRows + 1];
+  __shared__ int2 s_rc[2][kEdgeCap];                       // {rel, float_as_int(c)}
+  __shared__ __align__(16) int32_t s_src[USE_TMA ? 2 : 1][USE_TMA ? kEdgeCap + 8 : 1];
+  __shared__ __align__(16) int32_t s_rel[USE_TMA ? 2 : 1][USE_TMA ? kEdgeCap + 8 : 1];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * kRows;
+  const int nrows = (int)min((int64_t)kRows, p.Nt - r0);
+  const int D = p.D;
+
+  // ---------------- phase 1: stage row pointers + edge slice -----------------------------------------
+  if (tid <= nrows) {
+    s_rowptr[0][tid] = p.dir[0].rowptr[r0 + tid];
+    if (p.ndir == 2) s_rowptr[1][tid] = p.dir[1].rowptr[r0 + tid];
+  }
+  if (USE_TMA && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (USE_TMA) {
+    if (tid == 0) {
+      uint32_t total = 0;
+      uint32_t bytes[2];
+      int64_t abeg[2];
+      for (int d = 0; d < p.ndir; ++d) {
+        int64_t eb = s_rowptr[d][0], ee = s_rowptr[d][nrows];
+        int64_t ne = min(ee - eb, (int64_t)kEdgeCap);
+        abeg[d] = eb & ~(int64_t)3;
+        int64_t aend = min((eb + ne + 3) & ~(int64_t)3, p.Fpad);
+        bytes[d] = ne > 0 ? (uint32_t)((aend - abeg[d]) * 4) : 0u;
+        total += 2 * bytes[d];
+      }
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)),
+                   "r"(total)
+                   : "memory");
+      for (int d = 0; d < p.ndir; ++d) {
+        if (bytes[d] == 0) continue;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                "r"(smem_u32(&s_src[d][0])),
+            "l"(p.dir[d].src + abeg[d]), "r"(bytes[d]), "r"(smem_u32(&s_bar))
+            : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                "r"(smem_u32(&s_rel[d][0])),
+            "l"(p.dir[d].rel + abeg[d]), "r"(bytes[d]), "r"(smem_u32(&s_bar))
+            : "memory");
+      }
+    }
+    // everyone waits for the bulk copies (phase parity 0: the barrier is used once per CTA)
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(smem_u32(&s_bar)), "r"(0)
+          : "memory");
+    }
+  }
+  for (int d = 0; d < p.ndir; ++d) {
+    const AggDir& dd = p.dir[d];
+    const int64_t eb = s_rowptr[d][0];
+    const int ne = (int)min((int64_t)(s_rowptr[d][nrows] - eb), (int64_t)kEdgeCap);
+    const int shift = (int)(eb & 3);
+    for (int i = tid; i < ne; i += kThreads) {
+      int s, r;
+      if (USE_TMA) {
+        s = s_src[d][shift + i];
+        r = s_rel[d][shift + i];
+      } else {
+        s = dd.src ? dd.src[eb + i] : 0;
+        r = dd.rel[eb + i];
+      }
+      float c = edge_coeff<MODE>(p, dd, eb + i, s);
+      s_rc[d][i] = make_int2(r, __float_as_int(c));
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: one warp per destination row, lanes across features ----------------------
+  const int npass = (D + 32 * VEC - 1) / (32 * VEC);
+  for (int pass = 0; pass < npass; ++pass) {
+    const int col = pass * 32 * VEC + lane * VEC;
+    const bool active = col < D;
+    int cur_b = -1;
+    float insr[NI][VEC];
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) insr[j][k] = 0.f;
+
+    for (int lr = warp; lr < nrows; lr += kWarps) {
+      const int64_t row = r0 + lr;
+      if (MODE == MODE_MSG) {
+        const int b = (int)(row / p.N);
+        if (b != cur_b) {
+          cur_b = b;
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+              ldg_vec<VEC>(insr[j], p.ins + ((int64_t)b * p.I + p.j0 + j) * D + col);
+          }
+        }
+      }
+      float tsum[VEC];   // MODE_TYPE: sum over both directions
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) tsum[k] = 0.f;
+
+      for (int d = 0; d < p.ndir; ++d) {
+        const AggDir& dd = p.dir[d];
+        const int64_t ebase = s_rowptr[d][0];
+        const int beg = (int)(s_rowptr[d][lr] - ebase), end = (int)(s_rowptr[d][lr + 1] - ebase);
+        const float* __restrict__ table = dd.table;
+        float A[VEC], Bn[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) A[k] = Bn[k] = 0.f;
+        float csum = 0.f;
+
+        auto accumulate = [&](const float (&v)[VEC], float c) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            if (MODE == MODE_MSG) {
+              A[k] = fmaf(c, fmaxf(v[k], 0.f), A[k]);
+              Bn[k] = fmaf(c, fmaxf(-v[k], 0.f), Bn[k]);
+            } else {
+              A[k] = fmaf(c, v[k], A[k]);
+            }
+          }
+        };
+
+        int i = beg;
+        const int fast_end = min(end, kEdgeCap);
+        for (; i + 4 <= fast_end; i += 4) {
+          int2 m[4];
+          float v[4][VEC];
+          bool nz[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) m[u] = s_rc[d][i + u];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float c = __int_as_float(m[u].y);
+            nz[u] = (MODE == MODE_TYPE) || (c != 0.f);
+            if (nz[u] && active) ldg_vec<VEC>(v[u], table + (int64_t)m[u].x * D + col);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float c = __int_as_float(m[u].y);
+            csum += c;
+            if (nz[u] && active) accumulate(v[u], c);
+          }
+        }
+        for (; i < fast_end; ++i) {
+          int2 m = s_rc[d][i];
+          float c = __int_as_float(m.y);
+          csum += c;
+          if (((MODE == MODE_TYPE) || c != 0.f) && active) {
+            float v[VEC];
+            ldg_vec<VEC>(v, table + (int64_t)m.x * D + col);
+            accumulate(v, c);
+          }
+        }
+        for (; i < end; ++i) {   // slow path: tile's edge slice overflowed the staging buffer (hub rows)
+          const int64_t e = ebase + i;
+          const int s = dd.src ? dd.src[e] : 0;
+          const int r = dd.rel[e];
+          float c = edge_coeff<MODE>(p, dd, e, s);
+          csum += c;
+          if (((MODE == MODE_TYPE) || c != 0.f) && active) {
+            float v[VEC];
+            ldg_vec<VEC>(v, table + (int64_t)r * D + col);
+            accumulate(v, c);
+          }
+        }
+
+        if (MODE == MODE_MSG) {
+          if (active) {
+            float* o = p.out + row * p.out_row_stride + p.out_col0 + d * p.seg_stride_dir + col;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+              float y[VEC];
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) {
+                float x = insr[j][k];
+                y[k] = x >= 0.f ? x * A[k] : (-x) * Bn[k];
+              }
+              st_vec<VEC>(o + (int64_t)(p.j0 + j) * p.seg_stride_j, y);
+            }
+          }
+          if (p.possible && pass == 0 && d == 0 && lane == 0 && p.j0 == 0)
+            p.possible[row] = csum > 1e-10f ? 1.f : 0.f;   // nsm_gnn.py:101-103
+        } else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) tsum[k] += A[k];   // (sum_tail) + (sum_head), layer_init.py:57
+        }
+      }
+      if (MODE == MODE_TYPE && active) {
+        float y[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) y[k] = fmaxf(tsum[k], 0.f);
+        st_vec<VEC>(p.out + row * p.out_row_stride + p.out_col0 + col, y);
+      }
+    }
+  }
+}
+
+template <int VEC, int NI, int MODE>
+int launch_agg2(const AggParams& p, bool tma, cudaStream_t stream) {
+  unsigned grid = (unsigned)ceil_div(p.Nt, kRows);
+  if (tma)
+    agg_kernel<VEC, NI, MODE, true><<<grid, kThreads, 0, stream>>>(p);
+  else
+    agg_kernel<VEC, NI, MODE, false><<<grid, kThreads, 0, stream>>>(p);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
+template <int MODE>
+int launch_agg(AggParams p, cudaStream_t stream) {
+  // vector width from alignment of D, strides and base pointers
+  auto aligned = [&](int v) {
+    size_t a = (size_t)v * 4;
+    bool ok = p.D % v == 0 && p.out_row_stride % v == 0 && p.out_col0 % v == 0 &&
+              p.seg_stride_j % v == 0 && p.seg_stride_dir % v == 0 &&
+              (reinterpret_cast<size_t>(p.out) % a) == 0 && (reinterpret_cast<size_t>(p.ins) % a) == 0;
+    for (int d = 0; d < p.ndir; ++d) ok = ok && (reinterpret_cast<size_t>(p.dir[d].table) % a) == 0;
+    return ok;
+  };
+  int vec = aligned(4) ? 4 : (aligned(2) ? 2 : 1);
+  bool tma = g_opt_agg_tma != 0 && MODE == MODE_MSG;
+  for (int d = 0; d < p.ndir && tma; ++d)
+    tma = (reinterpret_cast<size_t>(p.dir[d].src) % 16) == 0 &&
+          (reinterpret_cast<size_t>(p.dir[d].rel) % 16) == 0;
+  if (MODE == MODE_TYPE) {
+    if (vec == 4) return launch_agg2<4, 1, MODE_TYPE>(p, false, stream);
+    if (vec == 2) return launch_agg2<2, 1, MODE_TYPE>(p, false, stream);
+    return launch_agg2<1, 1, MODE_TYPE>(p, false, stream);
+  }
+  const int I = p.I;
+  for (int j0 = 0; j0 < I; j0 += 4) {   // instructions in groups of <= 4 (epilogue register budget)
+    p.j0 = j0;
+    int ni = std::min(4, I - j0);
+    int rc;
+#define GR_AGG_CASE(V, NI_)                                             \
+  if (vec == V && ni == NI_) rc = launch_agg2<V, NI_, MODE_MSG>(p, tma, stream); else
+    GR_AGG_CASE(4, 1) GR_AGG_CASE(4, 2) GR_AGG_CASE(4, 3) GR_AGG_CASE(4, 4)
+    GR_AGG_CASE(2, 1) GR_AGG_CASE(2, 2) GR_AGG_CASE(2, 3) GR_AGG_CASE(2, 4)
+    GR_AGG_CASE(1, 1) GR_AGG_CASE(1, 2) GR_AGG_CASE(1, 3) GR_AGG_CASE(1, 4)
+    rc = GR_ERR_UNSUPPORTED;
+#undef GR_AGG_CASE
+    if (rc != GR_OK) return rc;
+  }
+  return GR_OK;
+}
+
+}  // namespace
+}  // namespace gr
+
+extern "C" int gr_aggregate(const int32_t* rowptr, const int32_t* src, const int32_t* rel,
+                            const float* w, const float* prior, const float* table, const float* ins,
+                            float* out, int64_t out_row_stride, int64_t out_col0, int64_t seg_stride,
+                            float* possible, int B, int N, int D, int I, int64_t F, void* stream_) {
+  using namespace gr;
+  GR_CHECK_ARG(rowptr && prior && table && ins && out, "null pointer");
+  GR_CHECK_ARG(F == 0 || (src && rel), "null edge arrays");
+  GR_CHECK_ARG(B > 0 && N > 0 && D > 0 && I > 0, "B, N, D, I must be positive");
+  AggParams p{};
+  p.dir[0] = AggDir{rowptr, src, rel, w, table};
+  p.ndir = 1;
+  p.prior = prior; p.ins = ins; p.out = out; p.possible = possible;
+  p.out_row_stride = out_row_stride; p.out_col0 = out_col0;
+  p.seg_stride_j = seg_stride; p.seg_stride_dir = 0;
+  p.B = B; p.N = N; p.D = D; p.I = I; p.j0 = 0;
+  p.Nt = (int64_t)B * N; p.Fpad = gr_pad4(F);
+  return launch_agg<MODE_MSG>(p, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t,
+                                 const float* w_t, const int32_t* rowptr_h, const int32_t* src_h,
+                                 const int32_t* rel_h, const float* w_h, const float* prior,
+                                 const float* table_fwd, const float* table_inv, const float* ins,
+                                 float* out, int64_t out_row_stride, int64_t out_col0, int B, int N,
+                                 int D, int I, int64_t F, void* stream_) {
+  using namespace gr;
+  GR_CHECK_ARG(rowptr_t && rowptr_h && prior && table_fwd && table_inv && ins && out, "null pointer");
+  GR_CHECK_ARG(F == 0 || (src_t && rel_t && src_h && rel_h), "null edge arrays");
+  GR_CHECK_ARG(B > 0 && N > 0 && D > 0 && I > 0, "B, N, D, I must be positive");
+  AggParams p{};
+  p.dir[0] = AggDir{rowptr_t, src_t, rel_t, w_t, table_fwd};
+  p.dir[1] = AggDir{rowptr_h, src_h, rel_h, w_h, table_inv};
+  p.ndir = 2;
+  p.prior = prior; p.ins = ins; p.out = out; p.possible = nullptr;
+  p.out_row_stride = out_row_stride; p.out_col0 = out_col0;
+  p.seg_stride_j = 2 * (int64_t)D; p.seg_stride_dir = D;
+  p.B = B; p.N = N; p.D = D; p.I = I; p.j0 = 0;
+  p.Nt = (int64_t)B * N; p.Fpad = gr_pad4(F);
+  return launch_agg<MODE_MSG>(p, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, const float* w_t,
+                             const int32_t* rowptr_h, const int32_t* rel_h, const float* w_h,
+                             const float* table, float* out, int64_t out_row_stride, int B, int N,
+                             int D, int64_t F, void* stream_) {
+  using namespace gr;
+  GR_CHECK_ARG(rowptr_t && rowptr_h && table && out, "null pointer");
+  GR_CHECK_ARG(F == 0 || (rel_t && rel_h), "null edge arrays");
+  GR_CHECK_ARG(B > 0 && N > 0 && D > 0, "B, N, D must be positive");
+  AggParams p{};
+  p.dir[0] = AggDir{rowptr_t, nullptr, rel_t, w_t, table};
+  p.dir[1] = AggDir{rowptr_h, nullptr, rel_h, w_h, table};
+  p.ndir = 2;
+  p.prior = nullptr; p.ins = nullptr; p.out = out; p.possible = nullptr;
+  p.out_row_stride = out_row_stride; p.out_col0 = 0;
+  p.seg_stride_j = 0; p.seg_stride_dir = 0;
+  p.B = B; p.N = N; p.D = D; p.I = 1; p.j0 = 0;
+  p.Nt = (int64_t)B * N; p.Fpad = gr_pad4(F);
+  return launch_agg<MODE_TYPE>(p, reinterpret_cast<cudaStream_t>(stream_));
+}

@@ -1,0 +1,127 @@
+"""Retrieved-answer-node sets and evaluation metrics, mirroring ``gnn/evaluate.py``.
+
+``retrieve`` is the candidate loop of ``Evaluator.evaluate`` (gnn/evaluate.py:188-209) plus the sort / eps-mass
+cut of ``f1_and_hits`` (:25-50), run on the device by csrc/rank.cu; only the short ordered candidate lists
+come back to the host.  ``Evaluator`` keeps the reference's class interface and ``.info`` JSONL row schema
+(:106-138, 210-219) so the downstream LLM stage (llm/src/qa_prediction) reads the output unchanged.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import batching, ops
+
+
+def retrieve(pred_dist, db, num_entity, eps):
+    """-> (per-question list of [(local_idx, entity_id, prob), ...] in retrieval order, d2h_bytes)."""
+    cand_idx, cand_count, _total = ops.rank_candidates(pred_dist, db.local_entity, db.query_entities,
+                                                       num_entity, eps)
+    counts = cand_count.cpu()
+    maxc = int(counts.max().item()) if counts.numel() else 0
+    out = []
+    if maxc == 0:
+        return [[] for _ in range(db.B)], counts.numel() * 4
+    idx = cand_idx[:, :maxc].long()
+    probs = torch.gather(pred_dist, 1, idx)
+    ents = torch.gather(db.local_entity, 1, idx)
+    idx_h, probs_h, ents_h = idx.cpu().numpy(), probs.cpu().numpy(), ents.cpu().numpy()
+    counts_h = counts.numpy()
+    for b in range(db.B):
+        c = int(counts_h[b])
+        out.append([(int(idx_h[b, i]), int(ents_h[b, i]), float(probs_h[b, i])) for i in range(c)])
+    d2h = counts.numel() * 4 + idx_h.size * 8 + probs_h.size * 4 + ents_h.size * 8
+    return out, d2h
+
+
+def f1_and_hits(answers, retrieved_ids):
+    """Metric tail of gnn/evaluate.py:51-67 on an already ordered + cut candidate list.
+    Returns (precision, recall, f1, hits, em, case)."""
+    best = retrieved_ids[0] if retrieved_ids else -1
+    correct = sum(1 for c in retrieved_ids if c in answers)
+    em = 1 if correct > 0 else 0
+    if len(answers) == 0:
+        return (1.0, 1.0, 1.0, 1.0, 1.0, 0) if not retrieved_ids else (0.0, 1.0, 0.0, 1.0, 1.0, 1)
+    hits = float(best in answers)
+    if not retrieved_ids:
+        return 1.0, 0.0, 0.0, hits, hits, 2
+    p, r = correct / len(retrieved_ids), correct / len(answers)
+    f1 = 2.0 / (1.0 / p + 1.0 / r) if p != 0 and r != 0 else 0.0
+    return p, r, f1, hits, em, 3
+
+
+class Evaluator:
+    """Drop-in for ``gnn/evaluate.py:Evaluator`` (constructor :70-104, ``evaluate`` :140-240)."""
+
+    def __init__(self, args, model, entity2id, relation2id, device):
+        self.model, self.args, self.eps = model, args, args["eps"]
+        self.model_name = args["model_name"]
+        self.id2entity = {idx: ent for ent, idx in entity2id.items()}
+        self.entity2name = None
+        self.device = device
+        self.file_write = None
+
+    def evaluate(self, valid_data, test_batch_size=20, write_info=False):
+        self.model.eval()
+        eps, id2entity = self.eps, self.id2entity
+        f1s, hits, ems, precisions, recalls = [], [], [], [], []
+        valid_data.reset_batches(is_sequential=True)
+        num_epoch = math.ceil(valid_data.num_data / test_batch_size)
+        if write_info and self.file_write is None:
+            path = os.path.join(self.args["checkpoint_dir"], "{}_test.info".format(self.args["experiment_name"]))
+            self.file_write = open(path, "w")
+        questions = valid_data.get_quest() if write_info else None
+        num_entity = len(id2entity)
+        row = 0
+        for it in range(num_epoch):
+            batch = valid_data.get_batch(it, test_batch_size, fact_dropout=0.0, test=True)
+            answer_lists = batch[-1]
+            with torch.no_grad():
+                _loss, _pred, pred_dist, _ = self.model(batch[:-1])
+            retrieved, _ = retrieve(pred_dist, self.model.last_batch, num_entity, eps)
+            for b, ret in enumerate(retrieved):
+                answers = list(answer_lists[b])
+                ids = [c for _, c, _ in ret]
+                p, r, f1, hit, em, _case = f1_and_hits(answers, ids)
+                if write_info:
+                    obj = {"question": questions[row]}
+                    for j in range(self.model.num_iter):
+                        obj[j] = {}
+                    obj.update({"answers": [id2entity[a] for a in answers], "precison": p, "recall": r,
+                                "f1": f1, "hit": hit, "em": em,
+                                "cand": [(id2entity[c], pr) for _, c, pr in ret]})
+                    self.file_write.write(json.dumps(obj) + "\n")
+                row += 1
+                f1s.append(f1); hits.append(hit); ems.append(em); precisions.append(p); recalls.append(r)
+        if write_info and self.file_write is not None:
+            self.file_write.close()
+            self.file_write = None
+        return float(np.mean(f1s)), float(np.mean(hits)), float(np.mean(ems))
+
+
+def path_node_sets(db, retrieved, max_targets=32):
+    """Shortest-path node sets seed -> retrieved candidates on the undirected subgraph
+    (llm/src/utils/graph_utils.py:10-21,49-75), computed on device (csrc/paths.cu).
+    Returns per-question sorted local-index lists and the [B,S,T] hop-distance tensor (host)."""
+    B, N = db.B, db.N
+    dev = db.local_entity.device
+    qe = db.query_entities
+    S = int(qe.sum(dim=1).max().item()) if B else 0
+    S = max(S, 1)
+    src_sorted = torch.argsort((qe != 0).to(torch.int8), dim=1, descending=True, stable=True)[:, :S]
+    source_idx = src_sorted.to(torch.int32).contiguous()
+    source_cnt = (qe != 0).sum(dim=1).to(torch.int32)
+    T = max(1, min(max_targets, max((len(r) for r in retrieved), default=1)))
+    tgt = np.zeros((B, T), dtype=np.int32)
+    cnt = np.zeros(B, dtype=np.int32)
+    for b, r in enumerate(retrieved):
+        k = min(len(r), T)
+        cnt[b] = k
+        tgt[b, :k] = [x[0] for x in r[:k]]
+    target_idx = torch.from_numpy(tgt).to(dev)
+    target_cnt = torch.from_numpy(cnt).to(dev)
+    on_path, pair_dist = ops.shortest_path_nodes(db.graph, source_idx, source_cnt, target_idx, target_cnt)
+    on = on_path.cpu().numpy()
+    return [np.nonzero(on[b])[0].tolist() for b in range(B)], pair_dist.cpu().numpy()

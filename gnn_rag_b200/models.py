@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's ``gnn/models``: ``ReaRev`` and ``NSM`` with the reference's
+constructor ``Model(args, num_entity, num_relation, num_word)``, ``forward(batch, training=False) ->
+(loss, pred, pred_dist, tp_list)``, parameter names (checkpoint layout ``{'model_state_dict': ...}``,
+gnn/train_model.py:236-252) and config keys (gnn/parsing.py) -- so the module drops into
+``Trainer_KBQA`` / ``Evaluator`` (gnn/train_model.py:49-57, gnn/evaluate.py:160).
+
+  BaseModel   gnn/models/base_model.py:10-297
+  ReaRev      gnn/models/ReaRev/rearev.py:19-244
+  NSM         gnn/models/NSM/nsm.py:19-254
+
+Inference only: ``training=True`` needs autograd through the CUDA kernels and raises.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import batching, ops
+from .modules import (AttnEncoder, Fusion, LSTMInstruction, NSMLayer, QueryReform, ReasonGNNLayer,
+                      TypeLayer)
+
+VERY_SMALL_NUMBER = 1e-10
+
+
+class BaseModel(nn.Module):
+    def __init__(self, args, num_entity, num_relation, num_word):
+        super().__init__()
+        self.num_relation, self.num_entity, self.num_word = num_relation, num_entity, num_word
+        self.kge_frozen = args["kge_frozen"]
+        self.kg_dim = args["kg_dim"]
+        self.entity_emb_file = args["entity_emb_file"]
+        self.relation_emb_file = args["relation_emb_file"]
+        self.relation_word_emb = args["relation_word_emb"]
+        self.word_emb_file = args["word_emb_file"]
+        self.entity_dim = args["entity_dim"]
+        self.lm = args["lm"]
+        if self.lm in ["bert"]:
+            args["word_dim"] = 768
+        self.word_dim = args["word_dim"]
+        self.rel_texts = None
+        self.device = torch.device("cuda" if args["use_cuda"] else "cpu")
+        for k, v in args.items():                                  # base_model.py:50-57
+            if k.endswith("dim"):
+                setattr(self, k, v)
+            if k.endswith("emb_file") or k.endswith("kge_file"):
+                setattr(self, k, None if v is None else args["data_folder"] + v)
+        self.use_inverse_relation = args.get("use_inverse_relation", False)
+        self.use_self_loop = args.get("use_self_loop", True)
+        self.eps = args["eps"]
+        self.loss_type = args.get("loss_type", "kl")
+        self.norm_rel = args["norm_rel"]
+        self.normalized_gnn = args["normalized_gnn"]
+        self._embedding_def()
+        args["word_dim"] = self.word_dim
+
+    # base_model.py:70-146
+    def _embedding_def(self):
+        ne, nr, nw = self.num_entity, self.num_relation, self.num_word
+        if self.lm != "lstm":
+            self.word_dim = 768
+            self.word_embedding = nn.Embedding(nw + 1, self.word_dim, padding_idx=nw)
+        elif self.word_emb_file is not None:
+            word_emb = np.load(self.word_emb_file)
+            self.word_dim = word_emb.shape[1]
+            self.word_embedding = nn.Embedding(nw + 1, self.word_dim, padding_idx=nw)
+            self.word_embedding.weight = nn.Parameter(
+                torch.from_numpy(np.pad(word_emb, ((0, 1), (0, 0)), "constant")).float(),
+                requires_grad=False)
+        else:
+            self.word_embedding = nn.Embedding(nw + 1, self.word_dim, padding_idx=nw)
+        if self.entity_emb_file is not None:
+            self.encode_type = False
+            emb = np.load(self.entity_emb_file)
+            ent_num, self.ent_dim = emb.shape
+            self.entity_embedding = nn.Embedding(ne + 1, self.ent_dim, padding_idx=ne)
+            if ent_num == ne:
+                self.entity_embedding.weight = nn.Parameter(
+                    torch.from_numpy(np.pad(emb, ((0, 1), (0, 0)), "constant")).float())
+            self.entity_embedding.weight.requires_grad = not self.kge_frozen
+        else:
+            self.ent_dim = self.kg_dim
+            self.encode_type = True
+        if self.relation_emb_file is not None:
+            half = np.load(self.relation_emb_file)
+            full = np.concatenate([half, half]) if self.use_inverse_relation else half
+            np_tensor = np.pad(full, ((0, 2 if self.use_self_loop else 0), (0, 0)), "constant")
+            rel_num, self.rel_dim = np_tensor.shape
+            self.relation_embedding = nn.Embedding(nr + 1, self.rel_dim)
+            if rel_num == nr:
+                self.relation_embedding.weight = nn.Parameter(torch.from_numpy(np_tensor).float())
+            self.relation_embedding.weight.requires_grad = not self.kge_frozen
+        elif self.relation_word_emb:
+            self.rel_dim = self.entity_dim
+            self.relation_embedding = nn.Embedding(nr + 1, self.rel_dim)
+            self.relation_embedding_inv = nn.Embedding(nr + 1, self.rel_dim)
+        else:
+            self.rel_dim = 2 * self.kg_dim
+            self.relation_embedding = nn.Embedding(nr + 1, self.rel_dim)
+            self.relation_embedding_inv = nn.Embedding(nr + 1, self.rel_dim)
+
+    def encode_rel_texts(self, rel_texts, rel_texts_inv):          # base_model.py:168-176
+        self.rel_texts = torch.from_numpy(rel_texts).long().to(self.device)
+        self.rel_texts_inv = torch.from_numpy(rel_texts_inv).long().to(self.device)
+        self.instruction.eval()
+        with torch.no_grad():
+            self.rel_features = self.instruction.encode_question(self.rel_texts, store=False)
+            self.rel_features_inv = self.instruction.encode_question(self.rel_texts_inv, store=False)
+
+    def _make_instruction(self, args):
+        if args["lm"] != "lstm":
+            raise NotImplementedError(
+                "lm=%r needs a HuggingFace encoder download (bert_encoder.py:31-78); this build ships the "
+                "LSTM question encoder only" % args["lm"])
+        return LSTMInstruction(args, self.word_embedding, self.num_word)
+
+    def _get_ent_init(self, db, rel_features, out):                # rearev.py:79-88 / nsm.py:84-94
+        if self.encode_type:
+            self.type_layer(db.graph, rel_features, out)
+        else:
+            emb = self.entity_embedding(db.local_entity).view(db.B * db.N, -1).contiguous()
+            ops.linear(emb, self.entity_linear.weight, self.entity_linear.bias, out=out)
+        return out
+
+    # base_model.py:186-215 + rearev.py:156-160
+    def calc_loss_label(self, curr_dist, teacher_dist, label_valid):
+        if self.loss_type == "bce":
+            tgt = (teacher_dist > 0).float() * 0.9
+            tp = F.binary_cross_entropy_with_logits(curr_dist, tgt, reduction="none")
+        else:
+            answer_len = torch.sum(teacher_dist, dim=1, keepdim=True)
+            answer_len = torch.where(answer_len == 0, torch.ones_like(answer_len), answer_len)
+            tp = F.kl_div(torch.log(curr_dist + 1e-8), teacher_dist / answer_len, reduction="none")
+        return torch.sum(tp * label_valid) / curr_dist.size(0)
+
+    def _check_ready(self, training):
+        if training:
+            raise NotImplementedError(
+                "gnn_rag_b200 implements the inference forward (forward + score); training needs the "
+                "backward of the aggregation kernel (SURVEY.md 8f row 4) -- train with the reference")
+        dev = self.word_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("gnn_rag_b200 models run on a CUDA device only (no CPU fallback); "
+                               "construct with args['use_cuda']=True / call .cuda()")
+        return dev
+
+
+class ReaRev(BaseModel):
+    def __init__(self, args, num_entity, num_relation, num_word):
+        super().__init__(args, num_entity, num_relation, num_word)
+        D = self.entity_dim
+        self.num_iter, self.num_ins, self.num_gnn = args["num_iter"], args["num_ins"], args["num_gnn"]
+        self.alg = args["alg"]
+        assert self.alg == "bfs"
+        self.linear_dropout = args["linear_dropout"]
+        self.entity_linear = nn.Linear(self.ent_dim, D)
+        self.relation_linear = nn.Linear(self.rel_dim, D)
+        self.linear_drop = nn.Dropout(p=self.linear_dropout)
+        if self.encode_type:
+            self.type_layer = TypeLayer(D, D, self.linear_drop, self.device, self.norm_rel)
+        self.self_att_r = AttnEncoder(D)
+        self.reasoning = ReasonGNNLayer(args, num_entity, num_relation, D, self.alg)
+        self.instruction = self._make_instruction(args)
+        if args["lm"] == "lstm":
+            self.relation_linear = nn.Linear(D, D)               # rearev.py:125
+        self.lin = nn.Linear(3 * D, D)                           # unused in forward (checkpoint compat)
+        self.fusion = Fusion(D)                                  # unused in forward (checkpoint compat)
+        for i in range(self.num_ins):
+            self.add_module("reform" + str(i), QueryReform(D))
+        self.to(self.device)
+
+    def get_rel_feature(self):                                   # rearev.py:91-111
+        if self.rel_texts is None:
+            lin = self.relation_linear
+            rel = ops.linear(self.relation_embedding.weight, lin.weight, lin.bias)
+            rel_inv = ops.linear(self.relation_embedding_inv.weight, lin.weight, lin.bias)
+            return rel, rel_inv
+        ins = self.instruction
+        rel = ins.question_emb(self.rel_features)
+        rel_inv = ins.question_emb(self.rel_features_inv)
+        rel = self.self_att_r(rel, (self.rel_texts != ins.pad_val).float())
+        rel_inv = self.self_att_r(rel_inv, (self.rel_texts != ins.pad_val).float())
+        return rel.contiguous(), rel_inv.contiguous()
+
+    @torch.no_grad()
+    def forward(self, batch, training=False):
+        """rearev.py:163-243.  ``batch`` = the ``get_batch`` tuple (host numpy) or a pre-staged
+        :class:`batching.DeviceBatch`."""
+        dev = self._check_ready(training)
+        D, I = self.entity_dim, self.num_ins
+        db = batching.stage_batch(batch, dev, self.num_relation + 1, self.normalized_gnn, self.norm_rel)
+        self.last_batch = db
+        B, N = db.B, db.N
+        rel_f, rel_f_inv = self.get_rel_feature()
+        self.reasoning.init_reason(db, rel_f, rel_f_inv)
+        self._get_ent_init(db, rel_f, self.reasoning.h_view)    # TypeLayer straight into X[:, :D]
+        instructions = self.instruction(db.q_input)              # rearev.py:192-196
+        self.dist_history = [db.seed_dist]
+        h = self.reasoning.h_view
+        for _t in range(self.num_iter):                          # rearev.py:206-221
+            relation_ins = torch.stack(instructions, dim=1)
+            dist = db.seed_dist                                  # distribution resets to the seed (:208)
+            for j in range(self.num_gnn):
+                dist, h = self.reasoning(dist, relation_ins, step=j)
+            self.dist_history.append(dist)
+            instructions = [getattr(self, "reform" + str(j))(instructions[j], h, db.query_entities, B, N)
+                            for j in range(I)]
+        pred_dist = self.dist_history[-1]
+        case_valid = (torch.sum(db.answer_dist, dim=1, keepdim=True) > 0).float()
+        loss = self.calc_loss_label(pred_dist, db.answer_dist, case_valid)
+        pred = torch.max(pred_dist, dim=1)[1]
+        return loss, pred, pred_dist, None
+
+
+class NSM(BaseModel):
+    def __init__(self, args, num_entity, num_relation, num_word):
+        super().__init__(args, num_entity, num_relation, num_word)
+        D = self.entity_dim
+        self.num_step = args["num_step"]
+        self.num_iter = self.num_step
+        self.model_name = args["model_name"].lower()
+        self.lambda_constrain, self.lambda_back = args["lambda_constrain"], args["lambda_back"]
+        if self.lambda_back != 0.0 or self.lambda_constrain != 0.0:
+            raise NotImplementedError("NSM backward-consistency branch is broken in the reference "
+                                      "(nsm_gnn.py:122 reads an unset attribute); not reproduced")
+        self.linear_dropout = args["linear_dropout"]
+        self.entity_linear = nn.Linear(self.ent_dim, D)
+        self.relation_linear1 = nn.Linear(self.rel_dim, D)
+        self.relation_linear2 = nn.Linear(self.rel_dim, D)       # unused in forward
+        self.kg_lin = nn.Linear(D, D)                            # unused in forward
+        self.score_func = nn.Linear(2 * D, 1)                    # unused in forward
+        self.linear_drop = nn.Dropout(p=self.linear_dropout)
+        if self.encode_type:
+            self.type_layer = TypeLayer(D, D, self.linear_drop, self.device, self.norm_rel)
+        self.self_att_r = AttnEncoder(D)
+        self.self_att_r2 = AttnEncoder(D)
+        self.reasoning = NSMLayer(args, num_entity, num_relation, D)
+        self.reasoning2 = NSMLayer(args, num_entity, num_relation, D)   # unused in forward (ckpt compat)
+        self.instruction = self._make_instruction(args)
+        self.to(self.device)
+
+    def get_rel_feature(self):                                   # nsm.py:97-111
+        lin = self.relation_linear1
+        return ops.linear(self.relation_embedding.weight, lin.weight, lin.bias)
+
+    @torch.no_grad()
+    def forward(self, batch, training=False):
+        """nsm.py:179-254 (forward reasoning only)."""
+        dev = self._check_ready(training)
+        db = batching.stage_batch(batch, dev, self.num_relation + 1, self.normalized_gnn, self.norm_rel)
+        self.last_batch = db
+        rel_f = self.get_rel_feature()
+        self.reasoning.init_reason(db, rel_f)
+        self._get_ent_init(db, rel_f, self.reasoning.h_view)
+        instruction_list = self.instruction(db.q_input)
+        dist = db.seed_dist
+        self.dist_history = [dist]
+        for i in range(self.num_step):                           # nsm.py:219-222
+            dist = self.reasoning(dist, instruction_list[i], step=i)
+            self.dist_history.append(dist)
+        pred_dist = self.dist_history[-1]
+        case_valid = (torch.sum(db.answer_dist, dim=1, keepdim=True) > 0).float()
+        loss = self.calc_loss_label(pred_dist, db.answer_dist, case_valid)
+        pred = torch.max(pred_dist, dim=1)[1]
+        return loss, pred, pred_dist, None

@@ -1,0 +1,250 @@
+"""Host-side mirror of the reference's ``gnn/modules`` for the retrieval hot path.
+
+Same class names, constructor arguments and parameter names as the reference so a reference
+``state_dict`` loads unchanged, but the graph work runs in the hand-written sm_100a kernels
+behind the C ABI (ops.py) instead of ``index_select`` / ``Linear``-over-facts / ``torch.sparse.mm``:
+
+  TypeLayer          gnn/modules/layer_init.py:8-65
+  AttnEncoder/Fusion/QueryReform   gnn/modules/query_update.py:6-61
+  LSTMInstruction    gnn/modules/question_encoding/{base,lstm}_encoder.py  (stays in PyTorch: O(B*Q*D), it
+                     feeds the path)
+  ReasonGNNLayer     gnn/modules/kg_reasoning/reasongnn.py:11-174
+  NSMLayer           gnn/modules/kg_reasoning/nsm_gnn.py:14-112
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+VERY_NEG_NUMBER = -100000000000
+
+
+class TypeLayer(nn.Module):
+    """h0[n] = relu(sum_{f: tail=n} v_f W rel[r_f] + sum_{f: head=n} v_f W rel[r_f])  (layer_init.py:25-62).
+    ``kb_self_linear`` is applied to the R1 relation rows once (hoisted) instead of to F gathered rows."""
+
+    def __init__(self, in_features, out_features, linear_drop, device, norm_rel):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.linear_drop = linear_drop
+        self.kb_self_linear = nn.Linear(in_features, out_features)
+        self.device = device
+        self.norm_rel = norm_rel
+
+    def forward(self, graph, rel_features, out):
+        table = ops.linear(rel_features, self.kb_self_linear.weight, self.kb_self_linear.bias)
+        wt, wh = (graph.wr_t, graph.wr_h) if self.norm_rel else (None, None)
+        ops.type_layer(graph, table, out, wt, wh)
+        return out
+
+
+class AttnEncoder(nn.Module):
+    """query_update.py:46-61 (relation-text pooling; dense, stays in PyTorch)."""
+
+    def __init__(self, d_hid):
+        super().__init__()
+        self.attn_linear = nn.Linear(d_hid, 1, bias=False)
+
+    def forward(self, x, x_mask):
+        a = self.attn_linear(x) - (1 - x_mask.unsqueeze(2)) * 1e8
+        return (x * F.softmax(a, dim=1)).sum(1)
+
+
+class Fusion(nn.Module):
+    """query_update.py:6-16: gate between instruction x and retrieved seed embedding y."""
+
+    def __init__(self, d_hid):
+        super().__init__()
+        self.r = nn.Linear(d_hid * 3, d_hid, bias=False)
+        self.g = nn.Linear(d_hid * 3, d_hid, bias=False)
+
+    def forward(self, x, y):
+        z = torch.cat([x, y, x - y], dim=-1)
+        g_ = torch.sigmoid(self.g(z))
+        return g_ * self.r(z) + (1 - g_) * x
+
+
+class QueryReform(nn.Module):
+    """query_update.py:18-44.  Only ``seed_retrieve`` reaches the output (the attention at :36-38 is dead
+    code); the seed-weighted row pick runs in csrc/score.cu and touches only the seed rows."""
+
+    def __init__(self, h_dim):
+        super().__init__()
+        self.fusion = Fusion(h_dim)
+        self.q_ent_attn = nn.Linear(h_dim, h_dim)   # kept for state_dict compatibility
+
+    def forward(self, q_node, h_view, seed_info, B, N):
+        seed_retrieve = ops.seed_retrieve(seed_info, h_view, B, N, q_node.shape[1])
+        return self.fusion(q_node, seed_retrieve)
+
+
+class LSTMInstruction(nn.Module):
+    """Question -> token states -> ``num_ins`` instruction vectors (lstm_encoder.py:10-45,
+    base_encoder.py:73-114).  Dropouts are identity in eval mode (the only mode this path supports)."""
+
+    def __init__(self, args, word_embedding, num_word):
+        super().__init__()
+        if "num_step" in args:                       # base_encoder.py:24-33
+            self.num_ins = args["num_step"]
+        elif "num_ins" in args:
+            self.num_ins = args["num_ins"]
+        else:
+            self.num_ins = 1
+        self.entity_dim = args["entity_dim"]
+        self.word_dim = args["word_dim"]
+        self.word_embedding = word_embedding
+        self.num_word = num_word
+        D = self.entity_dim
+        self.node_encoder = nn.LSTM(input_size=self.word_dim, hidden_size=D, batch_first=True,
+                                    bidirectional=False)
+        self.cq_linear = nn.Linear(4 * D, D)
+        self.ca_linear = nn.Linear(D, 1)
+        for i in range(self.num_ins):
+            self.add_module("question_linear" + str(i), nn.Linear(D, D))
+
+    def encode_question(self, query_text, store=True):
+        emb = self.word_embedding(query_text)
+        Bq = query_text.size(0)
+        z = torch.zeros(1, Bq, self.entity_dim, device=emb.device, dtype=emb.dtype)
+        hidden, (h_n, c_n) = self.node_encoder(emb, (z, z.clone()))
+        if not store:
+            return hidden
+        self.query_node_emb = h_n.squeeze(0).unsqueeze(1)
+        self.query_hidden_emb = hidden
+        self.query_mask = (query_text != self.num_word).float()
+        return hidden, self.query_node_emb
+
+    def init_reason(self, query_text):
+        self.encode_question(query_text)
+        self.relational_ins = torch.zeros(query_text.size(0), self.entity_dim, device=query_text.device)
+        self.instructions = []
+
+    def get_instruction(self, relational_ins, step=0):
+        ri = relational_ins.unsqueeze(1)
+        q_i = getattr(self, "question_linear" + str(step))(self.query_node_emb)
+        cq = self.cq_linear(torch.cat((ri, q_i, q_i - ri, q_i * ri), dim=-1))
+        ca = self.ca_linear(cq * self.query_hidden_emb)
+        attn = F.softmax(ca + (1 - self.query_mask.unsqueeze(2)) * VERY_NEG_NUMBER, dim=1)
+        return torch.sum(attn * self.query_hidden_emb, dim=1), attn
+
+    def forward(self, query_text):
+        self.init_reason(query_text)
+        out = []
+        for i in range(self.num_ins):
+            self.relational_ins, _ = self.get_instruction(self.relational_ins, step=i)
+            out.append(self.relational_ins)
+        return out
+
+
+class _GraphLayerBase(nn.Module):
+    """State shared by the two reasoning layers: activation ping-pong buffers X[2] of shape [B*N, Kd]
+    whose first D columns hold the node embeddings h and whose remaining columns receive the aggregated
+    neighbour messages -- the ``torch.cat`` of reasongnn.py:158-161 / nsm_gnn.py:62 is never materialised
+    by a copy, the aggregation kernel writes straight into its slot."""
+
+    def _alloc(self, Nt, Kd, device):
+        self.X = [torch.empty(Nt, Kd, dtype=torch.float32, device=device) for _ in range(2)]
+        self.cur = 0
+
+    @property
+    def h_view(self):
+        return self.X[self.cur][:, : self.entity_dim]
+
+
+class ReasonGNNLayer(_GraphLayerBase):
+    def __init__(self, args, num_entity, num_relation, entity_dim, alg):
+        super().__init__()
+        assert alg == "bfs"                                   # reasongnn.py:33
+        self.num_entity, self.num_relation, self.entity_dim = num_entity, num_relation, entity_dim
+        self.num_ins, self.num_gnn = args["num_ins"], args["num_gnn"]
+        self.use_posemb = args["pos_emb"]
+        self.normalized_gnn = args["normalized_gnn"]
+        D = entity_dim
+        self.score_func = nn.Linear(D, 1)
+        self.glob_lin = nn.Linear(D, D)                       # unused in forward, kept for the checkpoint
+        self.lin = nn.Linear(2 * D, D)                        # unused in forward
+        for i in range(self.num_gnn):
+            self.add_module("rel_linear" + str(i), nn.Linear(D, D))
+            self.add_module("e2e_linear" + str(i), nn.Linear(2 * self.num_ins * D + D, D))
+            if self.use_posemb:
+                self.add_module("pos_emb" + str(i), nn.Embedding(num_relation, D))
+                self.add_module("pos_emb_inv" + str(i), nn.Embedding(num_relation, D))
+        self.lin_m = nn.Linear(self.num_ins * D, D)           # unused in forward
+
+    def init_reason(self, db, rel_features, rel_features_inv):
+        """reasongnn.py:46-58.  Also builds the hoisted per-layer relation tables
+        P_k = rel_linear_k(rel_features) (+ pos_emb_k): 2*num_gnn small GEMMs per forward instead of one
+        Linear over F gathered rows per (iteration, layer, instruction, direction)."""
+        D = self.entity_dim
+        self.graph = db.graph
+        self.B, self.N = db.B, db.N
+        self.local_entity_mask = (db.local_entity != self.num_entity).float().view(-1)
+        self._alloc(db.B * db.N, (2 * self.num_ins + 1) * D, db.local_entity.device)
+        self.tables = []
+        for k in range(self.num_gnn):
+            lin = getattr(self, "rel_linear" + str(k))
+            pe = getattr(self, "pos_emb" + str(k)).weight if self.use_posemb else None
+            pei = getattr(self, "pos_emb_inv" + str(k)).weight if self.use_posemb else None
+            nrel = pe.shape[0] if pe is not None else 0
+            tf = ops.linear(rel_features, lin.weight, lin.bias, addend=pe, addend_rows=nrel)
+            ti = ops.linear(rel_features_inv, lin.weight, lin.bias, addend=pei, addend_rows=nrel)
+            self.tables.append((tf, ti))
+
+    def forward(self, current_dist, relational_ins, step=0):
+        """One GNN layer (reasongnn.py:134-174): aggregate both directions for every instruction into the
+        concat slots, h <- relu(e2e_k([h, nb...])), score, masked softmax."""
+        D = self.entity_dim
+        g = self.graph
+        X, Xn = self.X[self.cur], self.X[1 - self.cur]
+        tf, ti = self.tables[step]
+        wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
+        ops.aggregate_dual(g, current_dist, tf, ti, relational_ins, X, D, wt, wh)
+        e2e = getattr(self, "e2e_linear" + str(step))
+        ops.linear(X, e2e.weight, e2e.bias, relu=True, out=Xn[:, :D])
+        self.cur = 1 - self.cur
+        dist = ops.score_softmax(self.h_view, self.score_func.weight.view(-1), self.score_func.bias,
+                                 self.local_entity_mask, self.B, self.N)
+        return dist, self.h_view
+
+
+class NSMLayer(_GraphLayerBase):
+    def __init__(self, args, num_entity, num_relation, entity_dim):
+        super().__init__()
+        self.num_entity, self.num_relation, self.entity_dim = num_entity, num_relation, entity_dim
+        self.num_steps = args["num_step"]
+        self.reason_kb = args["reason_kb"]
+        self.normalized_gnn = args["normalized_gnn"]
+        D = entity_dim
+        self.score_func = nn.Linear(D, 1)
+        self.lin = nn.Linear(2 * D, D)                        # unused in forward
+        for i in range(self.num_steps):
+            self.add_module("rel_linear" + str(i), nn.Linear(D, D))
+            self.add_module("e2e_linear" + str(i), nn.Linear(2 * D, D))
+
+    def init_reason(self, db, rel_features):
+        D = self.entity_dim
+        self.graph = db.graph
+        self.B, self.N = db.B, db.N
+        self.local_entity_mask = (db.local_entity != self.num_entity).float().view(-1)
+        self._alloc(db.B * db.N, 2 * D, db.local_entity.device)
+        self.tables = []
+        for k in range(self.num_steps):
+            lin = getattr(self, "rel_linear" + str(k))
+            self.tables.append(ops.linear(rel_features, lin.weight, lin.bias))
+        self.possible = torch.empty(db.B * db.N, dtype=torch.float32, device=db.local_entity.device)
+
+    def forward(self, current_dist, relational_ins, step=0):
+        """nsm_gnn.py:54-77 + :87-112 (forward direction only, e2e: 2D -> D)."""
+        D = self.entity_dim
+        g = self.graph
+        X, Xn = self.X[self.cur], self.X[1 - self.cur]
+        w = g.w_t if self.normalized_gnn else None
+        ops.aggregate(g, "fwd", current_dist, self.tables[step], relational_ins.view(self.B, 1, D),
+                      out=X, out_col0=D, seg_stride=D, w=w, possible=self.possible)
+        e2e = getattr(self, "e2e_linear" + str(step))
+        ops.linear(X, e2e.weight, e2e.bias, relu=True, out=Xn[:, :D])
+        self.cur = 1 - self.cur
+        mask = self.local_entity_mask * self.possible if self.reason_kb else self.local_entity_mask
+        return ops.score_softmax(self.h_view, self.score_func.weight.view(-1), self.score_func.bias,
+                                 mask, self.B, self.N)

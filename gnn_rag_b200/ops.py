@@ -1,0 +1,271 @@
+"""Tensor-level wrappers over the C ABI (include/gnnrag_b200.h): torch CUDA tensors in, torch CUDA tensors
+out.  torch is used for device memory and streams only; every op below launches our own sm_100a kernels.
+All ops raise if handed a CPU tensor -- there is no CPU fallback on the product path."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+LINEAR_RELU = 1
+LINEAR_EXACT_FP32 = 2
+
+
+class _Stats:
+    """Launch accounting (bench.py's ``gpu_launches``) and optional CUDA-event timing of the aggregation
+    launches (bench.py's live roofline measurement).  Events are recorded on the launching stream."""
+
+    def __init__(self):
+        self.launches = 0
+        self.time_agg = False
+        self.agg_events = []      # (start_event, end_event, tag)
+
+    def reset(self):
+        self.launches = 0
+        self.agg_events = []
+
+
+STATS = _Stats()
+
+
+class _AggTimer:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if STATS.time_agg:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if STATS.time_agg:
+            self.e.record()
+            STATS.agg_events.append((self.s, self.e, self.tag))
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _cuda(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (no CPU fallback on this path)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def pad4(n):
+    return (n + 3) & ~3
+
+
+def set_option(name, value):
+    _lib.check(_L().gr_set_option(name.encode(), int(value)))
+
+
+class CsrGraph:
+    """Both destination-CSRs of one batched subgraph (device resident).
+
+    ``*_t``: in-edges grouped by tail (forward messages, src = head); ``*_h``: grouped by head (inverse
+    messages, src = tail).  ``fact_*`` maps a CSR slot back to the original fact id, so per-fact arrays
+    (weights) can be permuted with :func:`gather_f32`.
+    """
+
+    def __init__(self, B, N, F, R1, device):
+        self.B, self.N, self.F, self.R1 = B, N, F, R1
+        Nt = B * N
+        i32 = dict(dtype=torch.int32, device=device)
+        self.rowptr_t = torch.empty(pad4(Nt + 1), **i32)
+        self.rowptr_h = torch.empty(pad4(Nt + 1), **i32)
+        Fp = max(pad4(F), 4)
+        self.src_t = torch.empty(Fp, **i32)
+        self.rel_t = torch.empty(Fp, **i32)
+        self.fact_t = torch.empty(Fp, **i32)
+        self.src_h = torch.empty(Fp, **i32)
+        self.rel_h = torch.empty(Fp, **i32)
+        self.fact_h = torch.empty(Fp, **i32)
+        self.status = torch.zeros(1, **i32)
+        self.w_t = self.w_h = None        # normalized_gnn edge weights (1/outdeg(head))
+        self.wr_t = self.wr_h = None      # norm_rel edge weights (1/count(head, rel))
+
+    def check_status(self):
+        if int(self.status.item()) != 0:
+            raise RuntimeError("fact list contains node/relation ids outside the batch (clamped)")
+
+
+def csr_build(heads, rels, tails, B, N, R1):
+    """heads/rels/tails: 1-D int64 or int32 CUDA tensors (global rows b*N+local) -> CsrGraph."""
+    heads, rels, tails = _cuda(heads, name="heads"), _cuda(rels, name="rels"), _cuda(tails, name="tails")
+    if heads.dtype not in (torch.int64, torch.int32) or rels.dtype != heads.dtype or tails.dtype != heads.dtype:
+        raise RuntimeError("fact arrays must share dtype int64 or int32")
+    F = heads.numel()
+    g = CsrGraph(B, N, F, R1, heads.device)
+    L = _L()
+    ws_bytes = L.gr_csr_build_workspace_bytes(F, B * N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=heads.device)
+    rc = L.gr_csr_build(_p(heads.contiguous()), _p(rels.contiguous()), _p(tails.contiguous()),
+                        heads.element_size(), F, B * N, R1,
+                        _p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(g.fact_t),
+                        _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(g.fact_h),
+                        _p(g.status), _p(ws), ws_bytes, _stream())
+    _lib.check(rc)
+    STATS.launches += 9 if F > 0 else 5     # memsets excluded: hist, 3x scan, place, 2x sort, fill (+gather)
+    return g
+
+
+def gather_f32(values, fact):
+    values = _cuda(values, torch.float32, "values")
+    F = values.numel()
+    out = torch.empty(max(pad4(F), 4), dtype=torch.float32, device=values.device)
+    _lib.check(_L().gr_gather_f32(_p(values), _p(fact), _p(out), F, _stream()))
+    STATS.launches += 1
+    return out
+
+
+def linear(A, W, bias=None, relu=False, out=None, addend=None, addend_rows=0, exact=False):
+    """out[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ addend rows).  A/out may be strided row views."""
+    A, W = _cuda(A, torch.float32, "A"), _cuda(W, torch.float32, "W")
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and A.stride(1) == 1 and W.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    flags = (LINEAR_RELU if relu else 0) | (LINEAR_EXACT_FP32 if exact else 0)
+    rc = _L().gr_linear(_p(A), A.stride(0), _p(W), W.stride(0), _p(bias), _p(addend),
+                        addend.stride(0) if addend is not None else 0, addend_rows,
+                        _p(out), out.stride(0), M, N, K, flags, _stream())
+    _lib.check(rc)
+    STATS.launches += 1
+    return out
+
+
+def aggregate(g, direction, prior, table, ins, out=None, out_col0=0, seg_stride=None, w=None,
+              possible=None):
+    """One direction of the relation-typed aggregation.  direction: 'fwd' (tail CSR) | 'inv' (head CSR).
+    prior [B,N]; table [R1,D]; ins [B,I,D]; out [B*N, >= out_col0 + I*seg_stride] row-major view."""
+    prior = _cuda(prior, torch.float32, "prior").contiguous()
+    table = _cuda(table, torch.float32, "table").contiguous()
+    ins = _cuda(ins, torch.float32, "ins").contiguous()
+    B, I, D = ins.shape
+    N = g.N
+    if seg_stride is None:
+        seg_stride = D
+    if out is None:
+        out = torch.empty(B * N, I * seg_stride + out_col0, dtype=torch.float32, device=prior.device)
+    assert out.stride(1) == 1
+    if direction == "fwd":
+        rp, src, rel = g.rowptr_t, g.src_t, g.rel_t
+    else:
+        rp, src, rel = g.rowptr_h, g.src_h, g.rel_h
+    with _AggTimer(("single", I)):
+        rc = _L().gr_aggregate(_p(rp), _p(src), _p(rel), _p(w), _p(prior), _p(table), _p(ins), _p(out),
+                               out.stride(0), out_col0, seg_stride, _p(possible), B, N, D, I, g.F,
+                               _stream())
+    _lib.check(rc)
+    STATS.launches += (I + 3) // 4
+    return out
+
+
+def aggregate_dual(g, prior, table_fwd, table_inv, ins, out, out_col0, w_t=None, w_h=None):
+    """Both directions of one ReaRev layer: out[:, out_col0 + (2j+dir)*D : +D] (reasongnn.py:150-161)."""
+    prior = _cuda(prior, torch.float32, "prior").contiguous()
+    ins = _cuda(ins, torch.float32, "ins").contiguous()
+    B, I, D = ins.shape
+    assert out.stride(1) == 1 and table_fwd.is_contiguous() and table_inv.is_contiguous()
+    with _AggTimer(("dual", I)):
+        rc = _L().gr_aggregate_dual(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t),
+                                    _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(w_h),
+                                    _p(prior), _p(table_fwd), _p(table_inv), _p(ins), _p(out),
+                                    out.stride(0), out_col0, B, g.N, D, I, g.F, _stream())
+    _lib.check(rc)
+    STATS.launches += (I + 3) // 4
+    return out
+
+
+def type_layer(g, table, out, w_t=None, w_h=None):
+    """out[:, :D] = relu(sum_tail w*table[rel] + sum_head w*table[rel]) (layer_init.py:46-57)."""
+    table = _cuda(table, torch.float32, "table").contiguous()
+    D = table.shape[1]
+    assert out.stride(1) == 1
+    rc = _L().gr_type_layer(_p(g.rowptr_t), _p(g.rel_t), _p(w_t), _p(g.rowptr_h), _p(g.rel_h), _p(w_h),
+                            _p(table), _p(out), out.stride(0), g.B, g.N, D, g.F, _stream())
+    _lib.check(rc)
+    STATS.launches += 1
+    return out
+
+
+def score_softmax(h, w_score, b_score, mask, B, N, logits_out=None):
+    """h: [B*N, >=D] row view (stride(0) = ldh); returns dist [B,N]."""
+    h = _cuda(h, torch.float32, "h")
+    D = w_score.numel()
+    assert h.stride(1) == 1
+    dist = torch.empty(B, N, dtype=torch.float32, device=h.device)
+    rc = _L().gr_score_softmax(_p(h), h.stride(0), _p(w_score.contiguous()), _p(b_score),
+                               _p(mask.contiguous()), _p(dist), _p(logits_out), B, N, D, _stream())
+    _lib.check(rc)
+    STATS.launches += 2
+    return dist
+
+
+def seed_retrieve(seed_info, h, B, N, D):
+    seed_info = _cuda(seed_info, torch.float32, "seed_info").contiguous()
+    out = torch.empty(B, D, dtype=torch.float32, device=h.device)
+    assert h.stride(1) == 1
+    _lib.check(_L().gr_seed_retrieve(_p(seed_info), _p(h), h.stride(0), _p(out), B, N, D, _stream()))
+    STATS.launches += 1
+    return out
+
+
+def rank_candidates(dist, local_entity, query_entities, pad_id, eps):
+    """-> (cand_idx int32[B,N], cand_count int32[B], cand_total int32[B]) on device."""
+    dist = _cuda(dist, torch.float32, "dist").contiguous()
+    local_entity = _cuda(local_entity, torch.int64, "local_entity").contiguous()
+    query_entities = _cuda(query_entities, torch.float32, "query_entities").contiguous()
+    B, N = dist.shape
+    dev = dist.device
+    cand_idx = torch.empty(B, N, dtype=torch.int32, device=dev)
+    cand_count = torch.empty(B, dtype=torch.int32, device=dev)
+    cand_total = torch.empty(B, dtype=torch.int32, device=dev)
+    L = _L()
+    nbytes = L.gr_rank_workspace_bytes(B, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = L.gr_rank_candidates(_p(dist), _p(local_entity), _p(query_entities), int(pad_id), float(eps),
+                              _p(cand_idx), _p(cand_count), _p(cand_total), B, N, _p(ws), nbytes,
+                              _stream())
+    _lib.check(rc)
+    STATS.launches += 1
+    return cand_idx, cand_count, cand_total
+
+
+def shortest_path_nodes(g, source_idx, source_cnt, target_idx, target_cnt):
+    """source_idx int32[B,S], target_idx int32[B,T] local indices (+counts) ->
+    (on_path uint8[B,N], pair_dist int32[B,S,T])."""
+    B, N = g.B, g.N
+    S, T = source_idx.shape[1], target_idx.shape[1]
+    dev = source_idx.device
+    on_path = torch.empty(B, N, dtype=torch.uint8, device=dev)
+    pair_dist = torch.empty(B, S, T, dtype=torch.int32, device=dev)
+    L = _L()
+    nbytes = L.gr_paths_workspace_bytes(B, N, S, T)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = L.gr_shortest_path_nodes(_p(g.rowptr_t), _p(g.src_t), _p(g.rowptr_h), _p(g.src_h),
+                                  _p(source_idx.contiguous()), _p(source_cnt.contiguous()), S,
+                                  _p(target_idx.contiguous()), _p(target_cnt.contiguous()), T,
+                                  _p(on_path), _p(pair_dist), B, N, _p(ws), nbytes, _stream())
+    _lib.check(rc)
+    return on_path, pair_dist

@@ -1,0 +1,175 @@
+/*
+ * gnnrag_b200.h -- C ABI of libgnnrag_b200.so: the B200 (sm_100a) implementation of GNN-RAG's GNN
+ * retrieval hot path (ReaRev / NSM multi-hop message passing + answer scoring + candidate ranking).
+ *
+ * The reference (cmavro/GNN-RAG) has no FFI; its boundary is the Python nn.Module contract that
+ * gnn/train_model.py:49-57,222 and gnn/evaluate.py:160 call.  The Python mirror in gnn_rag_b200/ keeps
+ * that contract and calls the entry points below through ctypes.  Each entry point names the
+ * reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the CALLER allocates every input, output and workspace; the library never allocates, frees
+ *     or retains a pointer; it is stateless and re-entrant per stream;
+ *   - `stream` is a cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream);
+ *   - all work is enqueued asynchronously on `stream`; nothing synchronises;
+ *   - return value: 0 = GR_OK, negative = error (see gr_status); never throws;
+ *     gr_last_error() returns a thread-local message for the last failing call;
+ *   - node ids are GLOBAL rows b*N + local (gnn/dataset_load.py:483); index arrays produced by the
+ *     library are int32; floating point is fp32 unless stated;
+ *   - edge arrays (src/rel/w/fact) must be allocated with capacity gr_pad4(F) elements and row
+ *     pointer arrays with capacity gr_pad4(Nt + 1) elements (the staging copies read whole 16-byte
+ *     chunks).
+ */
+#ifndef GNNRAG_B200_H_
+#define GNNRAG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GR_ABI_VERSION 1
+
+typedef enum gr_status {
+  GR_OK = 0,
+  GR_ERR_INVALID_ARG = -1,   /* null pointer, bad size, unsupported combination            */
+  GR_ERR_CUDA = -2,          /* a CUDA runtime call failed (message in gr_last_error)        */
+  GR_ERR_WORKSPACE = -3,     /* workspace too small                                          */
+  GR_ERR_UNSUPPORTED = -4    /* shape/dtype not handled by this build                        */
+} gr_status;
+
+/* flags for gr_linear */
+#define GR_LINEAR_RELU 1u        /* C = relu(A W^T + b)                                      */
+#define GR_LINEAR_EXACT_FP32 2u  /* force the fp32 SIMT kernel (no split-bf16 tensor-core path) */
+
+int gr_abi_version(void);
+const char* gr_last_error(void);
+/* runtime switches: "agg_tma" (0|1: stage CSR slices with bulk TMA copies), "linear_tc" (0|1: split-bf16
+ * tcgen05 GEMM for gr_linear when the shape allows).  Process-wide; set before launching work. */
+int gr_set_option(const char* name, int64_t value);
+static inline int64_t gr_pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
+
+/* ------------------------------------------------------------------------------------------------
+ * CSR batching.  Replaces BaseGNNLayer.build_matrix (gnn/modules/kg_reasoning/base_gnn.py:19-51: seven
+ * uncoalesced COO tensors) and the index part of TypeLayer.forward (gnn/modules/layer_init.py:32-37).
+ * Input: the batched fact list of SingleDataLoader._build_fact_mat (gnn/dataset_load.py:473-527),
+ * copied to the device as-is (idx_bytes = 8 for the reference's int64 arrays, 4 for int32).
+ * Output: in-edges grouped by TAIL (forward messages: src = head) and by HEAD (inverse messages:
+ * src = tail); inside a row, edges keep the ORIGINAL FACT ORDER (stable), so per-row reductions are a
+ * pure function of the row's own fact sequence (deterministic; ties stay ties).
+ *   rowptr_*: int32[Nt+1]; src_*, rel_*, fact_*: int32[F] (fact_* = original fact id of each slot).
+ *   status: int32[1], set non-zero on device if an id is out of range (ids are clamped).
+ * Workspace: gr_csr_build_workspace_bytes(F, Nt).
+ */
+size_t gr_csr_build_workspace_bytes(int64_t F, int64_t Nt);
+int gr_csr_build(const void* heads, const void* rels, const void* tails, int idx_bytes,
+                 int64_t F, int64_t Nt, int64_t num_rel_rows,
+                 int32_t* rowptr_t, int32_t* src_t, int32_t* rel_t, int32_t* fact_t,
+                 int32_t* rowptr_h, int32_t* src_h, int32_t* rel_h, int32_t* fact_h,
+                 int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[e] = in[fact[e]] -- permute a per-fact fp32 array (weight_list / weight_rel_list of
+ * gnn/dataset_load.py:509-517) into CSR slot order. */
+int gr_gather_f32(const float* in, const int32_t* fact, float* out, int64_t F, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense linear layer  C[m, n] = act( sum_k A[m,k] W[n,k] + bias[n] ) (+ addend[m, n] for m < addend_rows)
+ * A: [M,K] row stride lda; W: [N,K] row stride ldw (torch nn.Linear layout); C: row stride ldc.
+ * Used for the HOISTED relation projection rel_linear_k(rel_features) (reasongnn.py:79,105 apply it to
+ * F gathered rows; the R1 distinct rows suffice), `addend` = pos_emb rows (reasongnn.py:75-77), and for
+ * e2e_linear (reasongnn.py:163, nsm_gnn.py:63).  bias / addend may be NULL.
+ */
+int gr_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+              const float* addend, int64_t ld_addend, int64_t addend_rows,
+              float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The aggregation kernel family.
+ *
+ * gr_aggregate: one direction.  For every destination row n and instruction j < I
+ *     out[n, out_col0 + j*seg_stride + d] = sum_{e in row n} relu(table[rel_e, d] * ins[b(n), j, d]) * c_e
+ *     c_e = w_e * (w_e * prior[src_e])        (w_e = 1 when w == NULL)
+ * = ReasonGNNLayer.reason_layer (reasongnn.py:61-89) with the tail CSR, reason_layer_inv (:91-116) with
+ * the head CSR, NSMLayer.reason_layer (nsm_gnn.py:87-112) with I = 1.  `table` is the hoisted
+ * rel_linear(rel_features) [R1, D].  ins: [B, I, D] contiguous.  b(n) = n / N.
+ * possible (optional, float[Nt]): 1.0 where sum_e c_e > 1e-10 (nsm_gnn.py:101-103).
+ * Edges with c_e == 0 are skipped exactly (relu(x)*0 = 0 for finite x).
+ *
+ * gr_aggregate_dual: both directions of one ReaRev GNN layer in one launch; instruction j writes
+ *     forward  (tail CSR, table_fwd) -> columns out_col0 + (2j  )*D
+ *     inverse  (head CSR, table_inv) -> columns out_col0 + (2j+1)*D
+ * which is the concat order of ReasonGNNLayer.forward (reasongnn.py:150-161).
+ *
+ * gr_type_layer: out[n,:] = relu( sum_{tail CSR} w_e table[rel_e] + sum_{head CSR} w_e table[rel_e] ),
+ * TypeLayer.forward (layer_init.py:46-57) with table = kb_self_linear(rel_features).
+ */
+int gr_aggregate(const int32_t* rowptr, const int32_t* src, const int32_t* rel, const float* w,
+                 const float* prior, const float* table, const float* ins,
+                 float* out, int64_t out_row_stride, int64_t out_col0, int64_t seg_stride,
+                 float* possible, int B, int N, int D, int I, int64_t F, void* stream);
+
+int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t,
+                      const float* w_t, const int32_t* rowptr_h, const int32_t* src_h,
+                      const int32_t* rel_h, const float* w_h, const float* prior,
+                      const float* table_fwd, const float* table_inv, const float* ins,
+                      float* out, int64_t out_row_stride, int64_t out_col0,
+                      int B, int N, int D, int I, int64_t F, void* stream);
+
+int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, const float* w_t,
+                  const int32_t* rowptr_h, const int32_t* rel_h, const float* w_h,
+                  const float* table, float* out, int64_t out_row_stride,
+                  int B, int N, int D, int64_t F, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scoring: logits[b,n] = dot(h[b,n,:], w_score) + b_score + (1 - mask[b,n]) * (-1e11);
+ * dist = softmax_n(logits).  reasongnn.py:165-169 / nsm_gnn.py:67-74.  One CTA per question.
+ * h row stride ldh.  mask: float[B*N] (local_entity != num_entity, times possible_tail for NSM
+ * reason_kb).  logits_out optional.
+ */
+int gr_score_softmax(const float* h, int64_t ldh, const float* w_score, const float* b_score,
+                     const float* mask, float* dist, float* logits_out, int B, int N, int D,
+                     void* stream);
+
+/* seed_retrieve[b,:] = sum_n seed_info[b,n] * h[b,n,:]  (torch.bmm in QueryReform.forward,
+ * gnn/modules/query_update.py:40); only rows with seed_info != 0 are read, in index order. */
+int gr_seed_retrieve(const float* seed_info, const float* h, int64_t ldh, float* out,
+                     int B, int N, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Candidate ranking = the retrieved answer-node set, Evaluator.evaluate + f1_and_hits
+ * (gnn/evaluate.py:156, 188-209, 25-50).  Per question: drop seeds (query_entities == 1), pads
+ * (local_entity == pad_id) and p < (1-eps)/N (compared in double); stable sort by p descending
+ * (ties keep local-index order); keep the prefix up to and including the item at which the
+ * sequential float64 running sum exceeds eps.
+ *   cand_idx:  int32[B, N]  local indices in retrieval order (first cand_count[b] valid)
+ *   cand_count:int32[B]; cand_total:int32[B] = number of candidates before the eps cut.
+ * Workspace: gr_rank_workspace_bytes(B, N).
+ */
+size_t gr_rank_workspace_bytes(int B, int N);
+int gr_rank_candidates(const float* dist, const int64_t* local_entity, const float* query_entities,
+                       int64_t pad_id, double eps, int32_t* cand_idx, int32_t* cand_count,
+                       int32_t* cand_total, int B, int N, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Shortest-path node sets: nodes lying on any shortest path between any seed and
+ * any retrieved candidate in the UNDIRECTED subgraph -- build_graph + get_truth_paths,
+ * llm/src/utils/graph_utils.py:10-21,49-75.  Uses both CSRs of a question batch; one CTA per question.
+ *   sources / targets: float[B*N] indicator arrays (non-zero = member).
+ *   on_path: uint8[B*N] output; dist_src: int32[B*N] workspace/output (BFS depth from the sources... see DESIGN.md)
+ */
+size_t gr_paths_workspace_bytes(int B, int N, int max_sources, int max_targets);
+int gr_shortest_path_nodes(const int32_t* rowptr_t, const int32_t* src_t,
+                           const int32_t* rowptr_h, const int32_t* src_h,
+                           const int32_t* source_idx, const int32_t* source_cnt, int max_sources,
+                           const int32_t* target_idx, const int32_t* target_cnt, int max_targets,
+                           uint8_t* on_path, int32_t* pair_dist, int B, int N,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNRAG_B200_H_ */

@@ -1,0 +1,106 @@
+"""CPU: host-side logic -- checkpoint (state_dict) compatibility with the reference, synthetic batch
+invariants, question sharding + gloo all-gather (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import gnn_rag_b200 as G
+from gnn_rag_b200 import parallel, synthetic as S
+from golden_io import Golden, names
+
+
+@pytest.mark.parametrize("name", names())
+def test_reference_state_dict_loads_strict(name):
+    g = Golden(name)
+    cls = G.NSM if g.args["model_name"] == "NSM" else G.ReaRev
+    m = cls(dict(g.args), g.num_entity, g.num_relation, g.num_word)
+    ours = m.state_dict()
+    assert set(ours) == set(g.sd), set(ours) ^ set(g.sd)
+    for k, v in g.sd.items():
+        assert tuple(ours[k].shape) == tuple(v.shape), k
+    m.load_state_dict(g.sd, strict=True)
+    # and the other way round: a checkpoint written by us has the reference layout
+    ck = {"model_state_dict": m.state_dict()}
+    assert list(ck["model_state_dict"].keys())
+
+
+def test_synthetic_batch_layout():
+    b = S.make_batch(3, B=4, N=30, E=80, num_entity=500, num_relation=12, num_word=50, n_real="ragged",
+                     multi_seed=True, test=True)
+    le, qe, kb, qi, sd, tb, ad, al = b
+    heads, rels, tails, bids, fids, wl, wrl = kb
+    assert le.dtype == np.int64 and qe.dtype == np.float64 and tb is None
+    assert np.allclose(sd.sum(1), 1.0)
+    assert (heads // 30 == bids).all() and (tails // 30 == bids).all()       # block diagonal
+    assert rels.max() == 11 and (rels[heads == tails].max() == 11)             # self loops use R-1
+    assert len(wl) == len(heads) == len(wrl)
+    real = le != 500
+    for q in range(4):                                                          # one self loop per real node
+        n_self = ((rels == 11) & (bids == q)).sum()
+        assert n_self == real[q].sum()
+    assert (fids == np.arange(len(heads))).all()
+
+
+def test_question_range_is_a_partition():
+    for B in (1, 7, 64, 1024):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.question_range(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_batch_reassembles():
+    b = S.make_batch(5, B=5, N=20, E=50, num_entity=300, num_relation=9, num_word=40)
+    N = 20
+    parts = [parallel.shard_batch(b, r, 2) for r in range(2)]
+    assert sum(p[0].shape[0] for p in parts) == 5
+    off = 0
+    got = []
+    for p in parts:
+        h, r, t = p[2][0], p[2][1], p[2][2]
+        assert h.min() >= 0 and h.max() < p[0].shape[0] * N
+        got.append(np.stack([h + off * N, r, t + off * N], 1))
+        off += p[0].shape[0]
+    got = np.concatenate(got)
+    want = np.stack([b[2][0], b[2][1], b[2][2]], 1)
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, B, N, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(B * N, dtype=torch.float32).view(B, N)
+    lo, hi = parallel.question_range(B, rank, world)
+    out = parallel.all_gather_scores(full[lo:hi].clone(), B)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [6, 7])
+def test_all_gather_scores_gloo_world2(B):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, B, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
