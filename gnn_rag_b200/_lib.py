@@ -26,6 +26,9 @@ SIGNATURES = {
     "gr_gather_f32": (c_int, [c_f32p, c_i32p, c_f32p, c_i64, c_void_p]),
     "gr_linear": (c_int, [c_f32p, c_i64, c_f32p, c_i64, c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_i64,
                           c_i64, c_i64, c_i64, c_u32, c_void_p]),
+    "gr_linear_tc_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "gr_linear_tc": (c_int, [c_f32p, c_i64, c_f32p, c_i64, c_f32p, c_f32p, c_i64, c_i64, c_i64, c_i64,
+                             c_u32, c_void_p, c_size, c_void_p]),
     "gr_aggregate": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64,
                              c_i64, c_i64, c_f32p, c_int, c_int, c_int, c_int, c_i64, c_void_p]),
     "gr_aggregate_dual": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p,

@@ -30,10 +30,10 @@ int g_opt_agg_tma = 0;   // set through gr_set_option("agg_tma", 0|1)
 
 namespace {
 
-constexpr int kRows = 32;        // destination rows per CTA tile
+constexpr int kRows = 64;        // destination rows per CTA tile
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kEdgeCap = 512;    // staged edges per direction per tile; the rest takes the slow path
+constexpr int kEdgeCap = 1024;   // staged edges per direction per tile; the rest takes the slow path
 
 enum { MODE_MSG = 0, MODE_TYPE = 1 };
 
@@ -63,7 +63,7 @@ template <> struct Vec<2> { using T = float2; };
 template <> struct Vec<1> { using T = float; };
 
 template <int VEC>
-__device__ __forceinline__ void ldg_vec(float (&v)[VEC], const float* p) {
+__device__ __forceinline__ void ldg_vec(float (&v)[VEC], const void* p) {
   using T = typename Vec<VEC>::T;
   T t = __ldg(reinterpret_cast<const T*>(p));
   const float* f = reinterpret_cast<const float*>(&t);
@@ -95,10 +95,39 @@ __device__ __forceinline__ float edge_coeff(const AggParams& p, const AggDir& d,
   return w * (w * pr);
 }
 
-template <int VEC, int NI, int MODE, bool USE_TMA>
-__global__ void __launch_bounds__(kThreads, 3) agg_kernel(const AggParams p) {
+// Two running sums per feature element, independent of the instruction:
+//   A = sum_e c_e * relu(v_e)     S = sum_e c_e * v_e       (=> sum_e c_e * relu(-v_e) = A - S)
+// accumulated with the packed fp32x2 FMA of sm_100 (FFMA2) when VEC is even.  If every v_e >= 0 the two
+// chains execute bit-identical operations, so A - S is exactly 0 where the true value is 0.
+template <int VEC, int MODE>
+__device__ __forceinline__ void accumulate(float (&A)[VEC], float (&S)[VEC], const float (&v)[VEC], float c) {
+  if (VEC % 2 == 0) {
+    const float2 cc = make_float2(c, c);
+#pragma unroll
+    for (int k = 0; k < VEC; k += 2) {
+      const float2 vv = make_float2(v[k], v[k + 1]);
+      float2 s2 = __ffma2_rn(cc, vv, make_float2(S[k], S[k + 1]));
+      S[k] = s2.x; S[k + 1] = s2.y;
+      if (MODE == MODE_MSG) {
+        const float2 vp = make_float2(fmaxf(vv.x, 0.f), fmaxf(vv.y, 0.f));
+        float2 a2 = __ffma2_rn(cc, vp, make_float2(A[k], A[k + 1]));
+        A[k] = a2.x; A[k + 1] = a2.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      S[k] = fmaf(c, v[k], S[k]);
+      if (MODE == MODE_MSG) A[k] = fmaf(c, fmaxf(v[k], 0.f), A[k]);
+    }
+  }
+}
+
+// CH = feature chunks per lane (1 or 2): one pass covers 32*VEC*CH columns.
+template <int VEC, int CH, int NI, int MODE, bool USE_TMA>
+__global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
   __shared__ int32_t s_rowptr[2][kRows + 1];
-  __shared__ int2 s_rc[2][kEdgeCap];                       // {rel, float_as_int(c)}
+  __shared__ int2 s_rc[2][kEdgeCap];                       // {table byte offset rel*D*4, float_as_int(c)}
   __shared__ __align__(16) int32_t s_src[USE_TMA ? 2 : 1][USE_TMA ? kEdgeCap + 8 : 1];
   __shared__ __align__(16) int32_t s_rel[USE_TMA ? 2 : 1][USE_TMA ? kEdgeCap + 8 : 1];
   __shared__ __align__(8) uint64_t s_bar;
@@ -106,7 +135,9 @@ __global__ void __launch_bounds__(kThreads, 3) agg_kernel(const AggParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * kRows;
   const int nrows = (int)min((int64_t)kRows, p.Nt - r0);
-  const int D = p.D;
+  const int D = p.D, N = p.N;
+  const int b0 = (int)(r0 / N);                 // one 64-bit division per thread per CTA
+  const int rem0 = (int)(r0 - (int64_t)b0 * N);
 
   // ---------------- phase 1: stage row pointers + edge slice -----------------------------------------
   if (tid <= nrows) {
@@ -175,144 +206,191 @@ __global__ void __launch_bounds__(kThreads, 3) agg_kernel(const AggParams p) {
         r = dd.rel[eb + i];
       }
       float c = edge_coeff<MODE>(p, dd, eb + i, s);
-      s_rc[d][i] = make_int2(r, __float_as_int(c));
+      s_rc[d][i] = make_int2((int)((uint32_t)r * (uint32_t)D * 4u), __float_as_int(c));
     }
   }
   __syncthreads();
 
   // ---------------- phase 2: one warp per destination row, lanes across features ----------------------
-  const int npass = (D + 32 * VEC - 1) / (32 * VEC);
-  for (int pass = 0; pass < npass; ++pass) {
-    const int col = pass * 32 * VEC + lane * VEC;
-    const bool active = col < D;
+  constexpr int PASS_COLS = 32 * VEC * CH;
+  for (int c0 = 0; c0 < D; c0 += PASS_COLS) {
+    int col[CH];
+    bool act[CH];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      col[ch] = c0 + ch * 32 * VEC + lane * VEC;
+      act[ch] = col[ch] < D;
+    }
+    // per-direction table column bases (64-bit) hoisted out of the row loop
+    const char* tcol[2][CH];
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch)
+        tcol[d][ch] = reinterpret_cast<const char*>(p.dir[d < p.ndir ? d : 0].table) + (size_t)col[ch] * 4;
+
     int cur_b = -1;
-    float insr[NI][VEC];
+    float insr[NI][CH][VEC];
 #pragma unroll
     for (int j = 0; j < NI; ++j)
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) insr[j][k] = 0.f;
+      for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) insr[j][ch][k] = 0.f;
+
+    float* const out_tile = p.out + r0 * p.out_row_stride + p.out_col0;
 
     for (int lr = warp; lr < nrows; lr += kWarps) {
-      const int64_t row = r0 + lr;
       if (MODE == MODE_MSG) {
-        const int b = (int)(row / p.N);
+        int q = rem0 + lr, b = b0;
+        while (q >= N) { q -= N; ++b; }
         if (b != cur_b) {
           cur_b = b;
-          if (active) {
 #pragma unroll
-            for (int j = 0; j < NI; ++j)
-              ldg_vec<VEC>(insr[j], p.ins + ((int64_t)b * p.I + p.j0 + j) * D + col);
-          }
+          for (int j = 0; j < NI; ++j)
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch)
+              if (act[ch]) ldg_vec<VEC>(insr[j][ch], p.ins + ((int64_t)b * p.I + p.j0 + j) * D + col[ch]);
         }
       }
-      float tsum[VEC];   // MODE_TYPE: sum over both directions
+      float* const orow = out_tile + (int64_t)lr * p.out_row_stride;
+      float tsum[CH][VEC];   // MODE_TYPE: sum over both directions
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) tsum[k] = 0.f;
+      for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) tsum[ch][k] = 0.f;
 
-      for (int d = 0; d < p.ndir; ++d) {
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        if (d >= p.ndir) break;
         const AggDir& dd = p.dir[d];
         const int64_t ebase = s_rowptr[d][0];
         const int beg = (int)(s_rowptr[d][lr] - ebase), end = (int)(s_rowptr[d][lr + 1] - ebase);
-        const float* __restrict__ table = dd.table;
-        float A[VEC], Bn[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) A[k] = Bn[k] = 0.f;
-        float csum = 0.f;
+        const int fast_end = min(end, kEdgeCap);
 
-        auto accumulate = [&](const float (&v)[VEC], float c) {
+        // does any edge of this row carry a non-zero coefficient?  (first layer of every iteration: the
+        // prior is the one-hot seed, almost every row is exactly zero -> pure zero store)
+        bool any = (MODE == MODE_TYPE) || (end > kEdgeCap);
+        if (MODE == MODE_MSG && !any) {
+          for (int i = beg + lane; i < fast_end; i += 32) any |= (s_rc[d][i].y << 1) != 0;   // c != +-0
+          any = __any_sync(0xffffffffu, any);
+        }
+        if (MODE == MODE_MSG && p.possible && c0 == 0 && d == 0 && p.j0 == 0) {   // nsm_gnn.py:101-103
+          float cs = 0.f;
+          for (int i = beg; i < fast_end; ++i) cs += __int_as_float(s_rc[d][i].y);
+          for (int i = max(beg, kEdgeCap); i < end; ++i)
+            cs += edge_coeff<MODE>(p, dd, ebase + i, dd.src[ebase + i]);
+          if (lane == 0) p.possible[r0 + lr] = cs > 1e-10f ? 1.f : 0.f;
+        }
+
+        float A[CH][VEC], S[CH][VEC];
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            if (MODE == MODE_MSG) {
-              A[k] = fmaf(c, fmaxf(v[k], 0.f), A[k]);
-              Bn[k] = fmaf(c, fmaxf(-v[k], 0.f), Bn[k]);
-            } else {
-              A[k] = fmaf(c, v[k], A[k]);
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) A[ch][k] = S[ch][k] = 0.f;
+
+        if (any) {
+          int i = beg;
+          for (; i + 4 <= fast_end; i += 4) {
+            int2 m[4];
+            float v[4][CH][VEC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m[u] = s_rc[d][i + u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch) {
+                if (act[ch]) {
+                  ldg_vec<VEC>(v[u][ch], tcol[d][ch] + (uint32_t)m[u].x);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < VEC; ++k) v[u][ch][k] = 0.f;
+                }
+              }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch)
+                accumulate<VEC, MODE>(A[ch], S[ch], v[u][ch], __int_as_float(m[u].y));
+          }
+          for (; i < fast_end; ++i) {
+            const int2 m = s_rc[d][i];
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+              float v[VEC];
+              if (act[ch]) {
+                ldg_vec<VEC>(v, tcol[d][ch] + (uint32_t)m.x);
+              } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) v[k] = 0.f;
+              }
+              accumulate<VEC, MODE>(A[ch], S[ch], v, __int_as_float(m.y));
             }
           }
-        };
-
-        int i = beg;
-        const int fast_end = min(end, kEdgeCap);
-        for (; i + 4 <= fast_end; i += 4) {
-          int2 m[4];
-          float v[4][VEC];
-          bool nz[4];
+          for (; i < end; ++i) {   // slow path: the tile's edge slice overflowed the staging buffer (hubs)
+            const int64_t e = ebase + i;
+            const int s = dd.src ? dd.src[e] : 0;
+            const uint32_t off = (uint32_t)dd.rel[e] * (uint32_t)D * 4u;
+            const float c = edge_coeff<MODE>(p, dd, e, s);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) m[u] = s_rc[d][i + u];
+            for (int ch = 0; ch < CH; ++ch) {
+              float v[VEC];
+              if (act[ch]) {
+                ldg_vec<VEC>(v, tcol[d][ch] + off);
+              } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float c = __int_as_float(m[u].y);
-            nz[u] = (MODE == MODE_TYPE) || (c != 0.f);
-            if (nz[u] && active) ldg_vec<VEC>(v[u], table + (int64_t)m[u].x * D + col);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float c = __int_as_float(m[u].y);
-            csum += c;
-            if (nz[u] && active) accumulate(v[u], c);
-          }
-        }
-        for (; i < fast_end; ++i) {
-          int2 m = s_rc[d][i];
-          float c = __int_as_float(m.y);
-          csum += c;
-          if (((MODE == MODE_TYPE) || c != 0.f) && active) {
-            float v[VEC];
-            ldg_vec<VEC>(v, table + (int64_t)m.x * D + col);
-            accumulate(v, c);
-          }
-        }
-        for (; i < end; ++i) {   // slow path: tile's edge slice overflowed the staging buffer (hub rows)
-          const int64_t e = ebase + i;
-          const int s = dd.src ? dd.src[e] : 0;
-          const int r = dd.rel[e];
-          float c = edge_coeff<MODE>(p, dd, e, s);
-          csum += c;
-          if (((MODE == MODE_TYPE) || c != 0.f) && active) {
-            float v[VEC];
-            ldg_vec<VEC>(v, table + (int64_t)r * D + col);
-            accumulate(v, c);
+                for (int k = 0; k < VEC; ++k) v[k] = 0.f;
+              }
+              accumulate<VEC, MODE>(A[ch], S[ch], v, c);
+            }
           }
         }
 
         if (MODE == MODE_MSG) {
-          if (active) {
-            float* o = p.out + row * p.out_row_stride + p.out_col0 + d * p.seg_stride_dir + col;
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            if (!act[ch]) continue;
+            float* o = orow + d * p.seg_stride_dir + col[ch];
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
               float y[VEC];
 #pragma unroll
               for (int k = 0; k < VEC; ++k) {
-                float x = insr[j][k];
-                y[k] = x >= 0.f ? x * A[k] : (-x) * Bn[k];
+                const float x = insr[j][ch][k];
+                const float t = x >= 0.f ? A[ch][k] : A[ch][k] - S[ch][k];   // sum c*relu(+-v)
+                y[k] = fabsf(x) * t;
               }
               st_vec<VEC>(o + (int64_t)(p.j0 + j) * p.seg_stride_j, y);
             }
           }
-          if (p.possible && pass == 0 && d == 0 && lane == 0 && p.j0 == 0)
-            p.possible[row] = csum > 1e-10f ? 1.f : 0.f;   // nsm_gnn.py:101-103
         } else {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) tsum[k] += A[k];   // (sum_tail) + (sum_head), layer_init.py:57
+          for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) tsum[ch][k] += S[ch][k];   // (sum_tail) + (sum_head), layer_init.py:57
         }
       }
-      if (MODE == MODE_TYPE && active) {
-        float y[VEC];
+      if (MODE == MODE_TYPE) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) y[k] = fmaxf(tsum[k], 0.f);
-        st_vec<VEC>(p.out + row * p.out_row_stride + p.out_col0 + col, y);
+        for (int ch = 0; ch < CH; ++ch) {
+          if (!act[ch]) continue;
+          float y[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) y[k] = fmaxf(tsum[ch][k], 0.f);
+          st_vec<VEC>(orow + col[ch], y);
+        }
       }
     }
   }
 }
 
-template <int VEC, int NI, int MODE>
+template <int VEC, int CH, int NI, int MODE>
 int launch_agg2(const AggParams& p, bool tma, cudaStream_t stream) {
   unsigned grid = (unsigned)ceil_div(p.Nt, kRows);
   if (tma)
-    agg_kernel<VEC, NI, MODE, true><<<grid, kThreads, 0, stream>>>(p);
+    agg_kernel<VEC, CH, NI, MODE, true><<<grid, kThreads, 0, stream>>>(p);
   else
-    agg_kernel<VEC, NI, MODE, false><<<grid, kThreads, 0, stream>>>(p);
+    agg_kernel<VEC, CH, NI, MODE, false><<<grid, kThreads, 0, stream>>>(p);
   GR_CHECK_LAUNCH();
   return GR_OK;
 }
@@ -328,26 +406,32 @@ int launch_agg(AggParams p, cudaStream_t stream) {
     for (int d = 0; d < p.ndir; ++d) ok = ok && (reinterpret_cast<size_t>(p.dir[d].table) % a) == 0;
     return ok;
   };
-  int vec = aligned(4) ? 4 : (aligned(2) ? 2 : 1);
+  const int vec = aligned(4) ? 4 : (aligned(2) ? 2 : 1);
+  const int ch = p.D > 32 * vec ? 2 : 1;
   bool tma = g_opt_agg_tma != 0 && MODE == MODE_MSG;
   for (int d = 0; d < p.ndir && tma; ++d)
     tma = (reinterpret_cast<size_t>(p.dir[d].src) % 16) == 0 &&
           (reinterpret_cast<size_t>(p.dir[d].rel) % 16) == 0;
   if (MODE == MODE_TYPE) {
-    if (vec == 4) return launch_agg2<4, 1, MODE_TYPE>(p, false, stream);
-    if (vec == 2) return launch_agg2<2, 1, MODE_TYPE>(p, false, stream);
-    return launch_agg2<1, 1, MODE_TYPE>(p, false, stream);
+#define GR_TYPE_CASE(V, C) if (vec == V && ch == C) return launch_agg2<V, C, 1, MODE_TYPE>(p, false, stream);
+    GR_TYPE_CASE(4, 1) GR_TYPE_CASE(4, 2) GR_TYPE_CASE(2, 1) GR_TYPE_CASE(2, 2) GR_TYPE_CASE(1, 1)
+    GR_TYPE_CASE(1, 2)
+#undef GR_TYPE_CASE
+    return GR_ERR_UNSUPPORTED;
   }
   const int I = p.I;
   for (int j0 = 0; j0 < I; j0 += 4) {   // instructions in groups of <= 4 (epilogue register budget)
     p.j0 = j0;
     int ni = std::min(4, I - j0);
     int rc;
-#define GR_AGG_CASE(V, NI_)                                             \
-  if (vec == V && ni == NI_) rc = launch_agg2<V, NI_, MODE_MSG>(p, tma, stream); else
-    GR_AGG_CASE(4, 1) GR_AGG_CASE(4, 2) GR_AGG_CASE(4, 3) GR_AGG_CASE(4, 4)
-    GR_AGG_CASE(2, 1) GR_AGG_CASE(2, 2) GR_AGG_CASE(2, 3) GR_AGG_CASE(2, 4)
-    GR_AGG_CASE(1, 1) GR_AGG_CASE(1, 2) GR_AGG_CASE(1, 3) GR_AGG_CASE(1, 4)
+#define GR_AGG_CASE(V, C, NI_)                                                       \
+  if (vec == V && ch == C && ni == NI_) rc = launch_agg2<V, C, NI_, MODE_MSG>(p, tma, stream); else
+    GR_AGG_CASE(4, 1, 1) GR_AGG_CASE(4, 1, 2) GR_AGG_CASE(4, 1, 3) GR_AGG_CASE(4, 1, 4)
+    GR_AGG_CASE(4, 2, 1) GR_AGG_CASE(4, 2, 2) GR_AGG_CASE(4, 2, 3) GR_AGG_CASE(4, 2, 4)
+    GR_AGG_CASE(2, 1, 1) GR_AGG_CASE(2, 1, 2) GR_AGG_CASE(2, 1, 3) GR_AGG_CASE(2, 1, 4)
+    GR_AGG_CASE(2, 2, 1) GR_AGG_CASE(2, 2, 2) GR_AGG_CASE(2, 2, 3) GR_AGG_CASE(2, 2, 4)
+    GR_AGG_CASE(1, 1, 1) GR_AGG_CASE(1, 1, 2) GR_AGG_CASE(1, 1, 3) GR_AGG_CASE(1, 1, 4)
+    GR_AGG_CASE(1, 2, 1) GR_AGG_CASE(1, 2, 2) GR_AGG_CASE(1, 2, 3) GR_AGG_CASE(1, 2, 4)
     rc = GR_ERR_UNSUPPORTED;
 #undef GR_AGG_CASE
     if (rc != GR_OK) return rc;

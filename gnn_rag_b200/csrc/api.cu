@@ -33,8 +33,6 @@ int linear_simt(const float* A, int64_t lda, const float* W, int64_t ldw, const 
                 const float* addend, int64_t ld_addend, int64_t addend_rows, float* C, int64_t ldc,
                 int64_t M, int64_t N, int64_t K, uint32_t flags, cudaStream_t stream);
 
-int g_opt_linear_tc = 0;
-
 }  // namespace gr
 
 extern "C" int gr_abi_version(void) { return GR_ABI_VERSION; }

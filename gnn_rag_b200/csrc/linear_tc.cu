@@ -1,0 +1,412 @@
+// Tensor-core linear layer for sm_100a:  C = act(A W^T + bias)  with fp32 in / fp32 out and fp32-class
+// accuracy, via the 3-product split-bf16 scheme on tcgen05:
+//     x = hi + lo (hi = bf16(x), lo = bf16(x - hi));   A W^T ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T
+// (dropped term A_lo W_lo^T <= 2^-18 relative).  All three products accumulate into one fp32 TMEM
+// accumulator.  This is the `e2e_linear` of ReasonGNNLayer.forward / NSMBaseLayer.forward
+// (reference gnn/modules/kg_reasoning/reasongnn.py:163, nsm_gnn.py:63): a genuine dense contraction,
+// M = B*N node rows, K = (2*num_ins+1)*D, N = D.
+//
+// Kernel: one CTA per 128-row tile of A, full N (<= 256) per CTA.  Warp roles (canonical Blackwell
+// GEMM): warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled K-major tiles of the four bf16
+// planes), warp 1 = MMA issuer (single thread, tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x Npad x 16,
+// 3 MMAs per K-step), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b, bias + relu,
+// stores).  smem ring of kStages {A_hi, A_lo, W_hi, W_lo} stages with full/empty mbarriers;
+// tcgen05.commit releases a stage and finally signals the epilogue.
+//
+// Roofline: tensor-pipe work 3 * 2*M*N*K flop; HBM traffic ~ 2 planes * M*K*2 B = M*K*4 B (same as fp32 A).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace gr {
+
+int g_opt_linear_tc = 0;   // gr_set_option("linear_tc", 0|1): route e2e linears through this kernel
+
+namespace {
+
+constexpr int BM = 128;          // rows per CTA tile == UMMA_M
+constexpr int BK = 64;           // bf16 elements per k-block == one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (row stride ld elements) -> tensor map with box {BK cols, box_rows},
+// 128-byte swizzle, zero fill out of bounds.
+bool make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) bf16 planes
+// ---------------------------------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int64_t K,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                  int64_t ldo, int vec_ok) {
+  const int64_t kq = (K + 3) / 4;
+  const int64_t total = M * kq;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t m = i / kq, k = (i - m * kq) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* src = A + m * lda + k;
+    if (vec_ok && k + 3 < K) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(src));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (k + q < K) v[q] = __ldg(src + q);
+    }
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      h[q] = __float2bfloat16_rn(v[q]);
+      l[q] = __float2bfloat16_rn(v[q] - __bfloat162float(h[q]));
+    }
+    __nv_bfloat16* ph = hi + m * ldo + k;
+    __nv_bfloat16* pl = lo + m * ldo + k;
+    if (k + 3 < ldo) {   // ldo is a multiple of 8: 8-byte aligned stores
+      *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<uint2*>(l);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (k + q < ldo) { ph[q] = h[q]; pl[q] = l[q]; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+  const float* bias;
+  float* C;
+  int64_t ldc;
+  int M, N, K, n_pad, stages, tmem_cols;
+  uint32_t flags;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages] x {A_hi 16K, A_lo 16K, W_hi n_pad*128, W_lo n_pad*128}, then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = BM * BK * 2;            // 16384
+  const int w_bytes = p.n_pad * BK * 2;       // n_pad * 128
+  const int stage_bytes = 2 * a_bytes + 2 * w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;                  // [stages]
+  uint64_t* empty_bar = bars + p.stages;      // [stages]
+  uint64_t* tmem_full_bar = bars + 2 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int nkb = (p.K + BK - 1) / BK;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t phase = 0;
+      int s = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+        tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m0);
+        tma_load_2d(st + a_bytes, &map_a_lo, &full_bar[s], kb * BK, m0);
+        tma_load_2d(st + 2 * a_bytes, &map_w_hi, &full_bar[s], kb * BK, 0);
+        tma_load_2d(st + 2 * a_bytes + w_bytes, &map_w_lo, &full_bar[s], kb * BK, 0);
+        if (++s == p.stages) { s = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n_pad
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      uint32_t phase = 0;
+      int s = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[s], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t da_hi = make_smem_desc(sa), da_lo = make_smem_desc(sa + a_bytes);
+        const uint64_t dw_hi = make_smem_desc(sa + 2 * a_bytes);
+        const uint64_t dw_lo = make_smem_desc(sa + 2 * a_bytes + w_bytes);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
+          umma_bf16(tmem_base, da_hi + adv, dw_hi + adv, idesc, (kb | k) ? 1u : 0u);
+          umma_bf16(tmem_base, da_hi + adv, dw_lo + adv, idesc, 1u);
+          umma_bf16(tmem_base, da_lo + adv, dw_hi + adv, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);               // frees this smem stage once the MMAs have read it
+        if (++s == p.stages) { s = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);                 // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const int64_t row = (int64_t)m0 + row_in_tile;
+    const bool relu = p.flags & GR_LINEAR_RELU;
+    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    float* crow = p.C + row * p.ldc;
+    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (row < p.M) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + j;
+          float x = __uint_as_float(r[j]);
+          if (col < p.N) {
+            if (p.bias) x += __ldg(p.bias + col);
+            if (relu) x = fmaxf(x, 0.f);
+          }
+          v[j] = x;
+        }
+        if (vec_ok && c0 + 16 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.N) crow[c0 + j] = v[j];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+struct TcPlan {
+  int64_t kp;          // plane row stride (elements), multiple of 8
+  int n_pad, stages, tmem_cols;
+  size_t a_plane_bytes, w_plane_bytes, total_bytes, smem_bytes;
+  bool ok;
+};
+
+TcPlan plan_tc(int64_t M, int64_t N, int64_t K) {
+  TcPlan t{};
+  t.ok = (N >= 8 && N <= 256 && K >= 8 && M >= 1);
+  t.kp = (K + 7) / 8 * 8;
+  t.n_pad = (int)((N + 15) / 16 * 16);
+  int cols = 32;
+  while (cols < t.n_pad) cols <<= 1;
+  t.tmem_cols = cols;
+  const size_t stage = 2 * (size_t)BM * BK * 2 + 2 * (size_t)t.n_pad * BK * 2;
+  int stages = (int)((200 * 1024) / stage);
+  t.stages = stages > 6 ? 6 : stages;
+  if (t.stages < 2) t.ok = false;
+  t.smem_bytes = (size_t)t.stages * stage + 1024 /*align slack*/ + (2 * t.stages + 2) * 8 + 16;
+  t.a_plane_bytes = align_up((size_t)M * t.kp * 2, 256);
+  t.w_plane_bytes = align_up((size_t)N * t.kp * 2, 256);
+  t.total_bytes = 2 * t.a_plane_bytes + 2 * t.w_plane_bytes;
+  return t;
+}
+
+}  // namespace
+
+bool linear_tc_supported(int64_t M, int64_t N, int64_t K) {
+  return plan_tc(M, N, K).ok && get_encode_fn() != nullptr;
+}
+
+}  // namespace gr
+
+extern "C" size_t gr_linear_tc_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return gr::plan_tc(M, N, K).total_bytes;
+}
+
+extern "C" int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                            float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, uint32_t flags,
+                            void* workspace, size_t workspace_bytes, void* stream_) {
+  using namespace gr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  GR_CHECK_ARG(A && W && C && workspace, "null pointer");
+  GR_CHECK_ARG(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
+  GR_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "leading dimension smaller than row length");
+  GR_CHECK_ARG(M < (int64_t)0x7fffffff - BM, "M exceeds int32 range");
+  TcPlan t = plan_tc(M, N, K);
+  if (!t.ok) {
+    set_error("gr_linear_tc: unsupported shape M=%lld N=%lld K=%lld (need 8 <= N <= 256, K >= 8)",
+              (long long)M, (long long)N, (long long)K);
+    return GR_ERR_UNSUPPORTED;
+  }
+  if (workspace_bytes < t.total_bytes) {
+    set_error("gr_linear_tc: workspace too small (%zu < %zu)", workspace_bytes, t.total_bytes);
+    return GR_ERR_WORKSPACE;
+  }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("gr_linear_tc: workspace must be 256-byte aligned");
+    return GR_ERR_INVALID_ARG;
+  }
+  char* ws = reinterpret_cast<char*>(workspace);
+  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* a_lo = reinterpret_cast<__nv_bfloat16*>(ws + t.a_plane_bytes);
+  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(ws + 2 * t.a_plane_bytes);
+  __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + 2 * t.a_plane_bytes + t.w_plane_bytes);
+  {
+    int va = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    int64_t work = M * ((K + 3) / 4);
+    int grid = (int)std::min<int64_t>(ceil_div(work, 256), 32LL * sm_count());
+    split_bf16_kernel<<<grid, 256, 0, stream>>>(A, lda, M, K, a_hi, a_lo, t.kp, va);
+    GR_CHECK_LAUNCH();
+    int vw = (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    work = N * ((K + 3) / 4);
+    grid = (int)std::min<int64_t>(ceil_div(work, 256), 32LL * sm_count());
+    split_bf16_kernel<<<grid, 256, 0, stream>>>(W, ldw, N, K, w_hi, w_lo, t.kp, vw);
+    GR_CHECK_LAUNCH();
+  }
+  CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
+  if (!make_tmap(&m_a_hi, a_hi, M, K, t.kp, BM) || !make_tmap(&m_a_lo, a_lo, M, K, t.kp, BM) ||
+      !make_tmap(&m_w_hi, w_hi, N, K, t.kp, t.n_pad) || !make_tmap(&m_w_lo, w_lo, N, K, t.kp, t.n_pad)) {
+    set_error("gr_linear_tc: cuTensorMapEncodeTiled failed");
+    return GR_ERR_CUDA;
+  }
+  TcParams p{};
+  p.bias = bias; p.C = C; p.ldc = ldc;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.n_pad = t.n_pad; p.stages = t.stages; p.tmem_cols = t.tmem_cols; p.flags = flags;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       220 * 1024));
+    attr_set = true;
+  }
+  unsigned grid = (unsigned)ceil_div(M, BM);
+  linear_tc_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, p);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}

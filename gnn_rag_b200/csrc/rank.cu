@@ -111,8 +111,8 @@ rank_kernel(const float* __restrict__ dist, const int64_t* __restrict__ local_en
     cand_total[b] = total;
   }
   // 4. ordered local indices
-  for (int i = tid; i < total; i += kRankThreads)
-    cand_idx[(int64_t)b * N + i] = (int32_t)(keys[i] & 0xFFFFFFFFull);
+  for (int i = tid; i < N; i += kRankThreads)   // slots past `total` are zero-filled (defined output)
+    cand_idx[(int64_t)b * N + i] = i < total ? (int32_t)(keys[i] & 0xFFFFFFFFull) : 0;
 }
 
 }  // namespace

@@ -15,24 +15,38 @@ import torch
 from . import batching, ops
 
 
+class Retrieved:
+    """Retrieved candidates of one question, in retrieval order (numpy views, no per-item Python objects):
+    ``idx`` local node indices, ``ent`` global entity ids, ``prob`` fp32 probabilities."""
+    __slots__ = ("idx", "ent", "prob")
+
+    def __init__(self, idx, ent, prob):
+        self.idx, self.ent, self.prob = idx, ent, prob
+
+    def __len__(self):
+        return len(self.idx)
+
+    def pairs(self):
+        """[(entity_id, prob_as_python_float), ...] -- the reference's ``retrieved`` list layout."""
+        return list(zip(self.ent.tolist(), self.prob.astype(np.float64).tolist()))
+
+
 def retrieve(pred_dist, db, num_entity, eps):
-    """-> (per-question list of [(local_idx, entity_id, prob), ...] in retrieval order, d2h_bytes)."""
+    """Device ranking (csrc/rank.cu) + one D2H of the ordered lists.
+    -> (list of :class:`Retrieved`, one per question; d2h_bytes)."""
     cand_idx, cand_count, _total = ops.rank_candidates(pred_dist, db.local_entity, db.query_entities,
                                                        num_entity, eps)
-    counts = cand_count.cpu()
-    maxc = int(counts.max().item()) if counts.numel() else 0
-    out = []
+    counts_h = cand_count.cpu().numpy()
+    maxc = int(counts_h.max()) if counts_h.size else 0
+    empty_i, empty_f = np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float32)
     if maxc == 0:
-        return [[] for _ in range(db.B)], counts.numel() * 4
+        return [Retrieved(empty_i, empty_i, empty_f) for _ in range(db.B)], counts_h.size * 4
     idx = cand_idx[:, :maxc].long()
     probs = torch.gather(pred_dist, 1, idx)
     ents = torch.gather(db.local_entity, 1, idx)
     idx_h, probs_h, ents_h = idx.cpu().numpy(), probs.cpu().numpy(), ents.cpu().numpy()
-    counts_h = counts.numpy()
-    for b in range(db.B):
-        c = int(counts_h[b])
-        out.append([(int(idx_h[b, i]), int(ents_h[b, i]), float(probs_h[b, i])) for i in range(c)])
-    d2h = counts.numel() * 4 + idx_h.size * 8 + probs_h.size * 4 + ents_h.size * 8
+    out = [Retrieved(idx_h[b, :c], ents_h[b, :c], probs_h[b, :c]) for b, c in enumerate(counts_h.tolist())]
+    d2h = counts_h.size * 4 + idx_h.size * 8 + probs_h.size * 4 + ents_h.size * 8
     return out, d2h
 
 
@@ -83,7 +97,7 @@ class Evaluator:
             retrieved, _ = retrieve(pred_dist, self.model.last_batch, num_entity, eps)
             for b, ret in enumerate(retrieved):
                 answers = list(answer_lists[b])
-                ids = [c for _, c, _ in ret]
+                ids = ret.ent.tolist()
                 p, r, f1, hit, em, _case = f1_and_hits(answers, ids)
                 if write_info:
                     obj = {"question": questions[row]}
@@ -91,7 +105,7 @@ class Evaluator:
                         obj[j] = {}
                     obj.update({"answers": [id2entity[a] for a in answers], "precison": p, "recall": r,
                                 "f1": f1, "hit": hit, "em": em,
-                                "cand": [(id2entity[c], pr) for _, c, pr in ret]})
+                                "cand": [(id2entity[c], pr) for c, pr in ret.pairs()]})
                     self.file_write.write(json.dumps(obj) + "\n")
                 row += 1
                 f1s.append(f1); hits.append(hit); ems.append(em); precisions.append(p); recalls.append(r)
@@ -119,7 +133,7 @@ def path_node_sets(db, retrieved, max_targets=32):
     for b, r in enumerate(retrieved):
         k = min(len(r), T)
         cnt[b] = k
-        tgt[b, :k] = [x[0] for x in r[:k]]
+        tgt[b, :k] = np.asarray(r.idx[:k] if isinstance(r, Retrieved) else [x[0] for x in r[:k]])
     target_idx = torch.from_numpy(tgt).to(dev)
     target_cnt = torch.from_numpy(cnt).to(dev)
     on_path, pair_dist = ops.shortest_path_nodes(db.graph, source_idx, source_cnt, target_idx, target_cnt)

@@ -107,7 +107,8 @@ class LSTMInstruction(nn.Module):
         emb = self.word_embedding(query_text)
         Bq = query_text.size(0)
         z = torch.zeros(1, Bq, self.entity_dim, device=emb.device, dtype=emb.dtype)
-        hidden, (h_n, c_n) = self.node_encoder(emb, (z, z.clone()))
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # keep the encoder fp32-exact
+            hidden, (h_n, c_n) = self.node_encoder(emb, (z, z.clone()))
         if not store:
             return hidden
         self.query_node_emb = h_n.squeeze(0).unsqueeze(1)
@@ -201,7 +202,7 @@ class ReasonGNNLayer(_GraphLayerBase):
         wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
         ops.aggregate_dual(g, current_dist, tf, ti, relational_ins, X, D, wt, wh)
         e2e = getattr(self, "e2e_linear" + str(step))
-        ops.linear(X, e2e.weight, e2e.bias, relu=True, out=Xn[:, :D])
+        ops.e2e_linear(X, e2e.weight, e2e.bias, Xn[:, :D])
         self.cur = 1 - self.cur
         dist = ops.score_softmax(self.h_view, self.score_func.weight.view(-1), self.score_func.bias,
                                  self.local_entity_mask, self.B, self.N)
@@ -243,7 +244,7 @@ class NSMLayer(_GraphLayerBase):
         ops.aggregate(g, "fwd", current_dist, self.tables[step], relational_ins.view(self.B, 1, D),
                       out=X, out_col0=D, seg_stride=D, w=w, possible=self.possible)
         e2e = getattr(self, "e2e_linear" + str(step))
-        ops.linear(X, e2e.weight, e2e.bias, relu=True, out=Xn[:, :D])
+        ops.e2e_linear(X, e2e.weight, e2e.bias, Xn[:, :D])
         self.cur = 1 - self.cur
         mask = self.local_entity_mask * self.possible if self.reason_kb else self.local_entity_mask
         return ops.score_softmax(self.h_view, self.score_func.weight.view(-1), self.score_func.bias,

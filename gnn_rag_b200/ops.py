@@ -154,6 +154,35 @@ def linear(A, W, bias=None, relu=False, out=None, addend=None, addend_rows=0, ex
     return out
 
 
+TC_LINEAR = True       # route the big e2e linears through the tcgen05 split-bf16 kernel (models use this)
+
+
+def linear_tc(A, W, bias=None, relu=False, out=None):
+    """Tensor-core (tcgen05, split-bf16 x3) version of :func:`linear` for 8 <= N <= 256."""
+    A, W = _cuda(A, torch.float32, "A"), _cuda(W, torch.float32, "W")
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and A.stride(1) == 1 and W.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    L = _L()
+    nbytes = L.gr_linear_tc_workspace_bytes(M, N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    rc = L.gr_linear_tc(_p(A), A.stride(0), _p(W), W.stride(0), _p(bias), _p(out), out.stride(0),
+                        M, N, K, LINEAR_RELU if relu else 0, _p(ws), nbytes, _stream())
+    _lib.check(rc)
+    STATS.launches += 3
+    return out
+
+
+def e2e_linear(A, W, bias, out):
+    """relu(A W^T + b) for the node-update GEMM: tcgen05 path when enabled and the shape fits."""
+    if TC_LINEAR and 8 <= W.shape[0] <= 256 and W.shape[1] >= 8:
+        return linear_tc(A, W, bias, relu=True, out=out)
+    return linear(A, W, bias, relu=True, out=out)
+
+
 def aggregate(g, direction, prior, table, ins, out=None, out_col0=0, seg_stride=None, w=None,
               possible=None):
     """One direction of the relation-typed aggregation.  direction: 'fwd' (tail CSR) | 'inv' (head CSR).

@@ -86,6 +86,17 @@ int gr_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
               const float* addend, int64_t ld_addend, int64_t addend_rows,
               float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, uint32_t flags, void* stream);
 
+/* Tensor-core variant of gr_linear for the big e2e_linear GEMMs (reasongnn.py:163, nsm_gnn.py:63):
+ * fp32 in / fp32 out with fp32-class accuracy through the 3-product split-bf16 scheme on tcgen05
+ * (x = hi + lo in bf16; A W^T ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T, fp32 accumulation in TMEM,
+ * dropped term <= 2^-18 relative).  TMA-fed, 128 x N x 64 tiles, one CTA per 128 rows.  Requires
+ * 8 <= N <= 256.  The workspace (256-byte aligned, gr_linear_tc_workspace_bytes) holds the bf16 planes.
+ * flags: GR_LINEAR_RELU. */
+size_t gr_linear_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                 float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, uint32_t flags,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * The aggregation kernel family.
  *
