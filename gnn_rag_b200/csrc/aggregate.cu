@@ -22,6 +22,8 @@
 //
 // Roofline: HBM-bound on the OUTPUT rows: per (direction, instruction) unit
 //   F*8 + (Nt+1)*4 + Nt*4 + R1*D*4 + B*D*4 + Nt*D*4 bytes.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gr {
@@ -50,7 +52,10 @@ struct AggParams {
   int ndir;
   const float* prior;
   const float* ins;     // [B, I, D]
-  float* out;
+  float* out;               // fp32 output (may be null when the bf16 planes are requested)
+  __nv_bfloat16* out_hi;    // optional split-bf16 planes (hi + lo ~= value to 2^-18): the A operand layout of
+  __nv_bfloat16* out_lo;    // the tcgen05 e2e GEMM (linear_tc.cu); same column indexing as `out`
+  int64_t ld_planes;
   float* possible;
   int64_t out_row_stride, out_col0, seg_stride_j, seg_stride_dir;
   int B, N, D, I, j0;   // this launch handles instructions j0 .. j0+NI-1
@@ -85,6 +90,27 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// y -> (hi, lo) bf16 pair per element, hi = bf16(y), lo = bf16(y - hi); vector store of VEC elements each
+template <int VEC>
+__device__ __forceinline__ void st_split(__nv_bfloat16* ph, __nv_bfloat16* pl, const float (&y)[VEC]) {
+  __align__(8) __nv_bfloat16 h[VEC], l[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    h[k] = __float2bfloat16_rn(y[k]);
+    l[k] = __float2bfloat16_rn(y[k] - __bfloat162float(h[k]));
+  }
+  if (VEC == 4) {
+    *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<const uint2*>(l);
+  } else if (VEC == 2) {
+    *reinterpret_cast<uint32_t*>(ph) = *reinterpret_cast<const uint32_t*>(h);
+    *reinterpret_cast<uint32_t*>(pl) = *reinterpret_cast<const uint32_t*>(l);
+  } else {
+    ph[0] = h[0];
+    pl[0] = l[0];
+  }
+}
+
 // coefficient of one edge: c = w*(w*prior[src]) (reasongnn.py:80-84 applies the COO value twice when
 // normalized_gnn is on); TypeLayer: c = w (layer_init.py:39-42,52-53)
 template <int MODE>
@@ -101,7 +127,7 @@ __device__ __forceinline__ float edge_coeff(const AggParams& p, const AggDir& d,
 // chains execute bit-identical operations, so A - S is exactly 0 where the true value is 0.
 template <int VEC, int MODE>
 __device__ __forceinline__ void accumulate(float (&A)[VEC], float (&S)[VEC], const float (&v)[VEC], float c) {
-  if (VEC % 2 == 0) {
+  if constexpr (VEC % 2 == 0) {
     const float2 cc = make_float2(c, c);
 #pragma unroll
     for (int k = 0; k < VEC; k += 2) {
@@ -120,6 +146,23 @@ __device__ __forceinline__ void accumulate(float (&A)[VEC], float (&S)[VEC], con
       S[k] = fmaf(c, v[k], S[k]);
       if (MODE == MODE_MSG) A[k] = fmaf(c, fmaxf(v[k], 0.f), A[k]);
     }
+  }
+}
+
+// y = xp * A + xn * (A - S)   with xp = relu(x), xn = relu(-x)   (exactly one of xp, xn is non-zero)
+template <int VEC>
+__device__ __forceinline__ void msg_epilogue(float (&y)[VEC], const float (&xp)[VEC], const float (&xn)[VEC],
+                                             const float (&A)[VEC], const float (&T)[VEC]) {
+  if constexpr (VEC % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < VEC; k += 2) {
+      float2 r = __fmul2_rn(make_float2(xp[k], xp[k + 1]), make_float2(A[k], A[k + 1]));
+      r = __ffma2_rn(make_float2(xn[k], xn[k + 1]), make_float2(T[k], T[k + 1]), r);
+      y[k] = r.x; y[k + 1] = r.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) y[k] = fmaf(xn[k], T[k], xp[k] * A[k]);
   }
 }
 
@@ -213,32 +256,42 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
 
   // ---------------- phase 2: one warp per destination row, lanes across features ----------------------
   constexpr int PASS_COLS = 32 * VEC * CH;
+  const bool to_f32 = p.out != nullptr, to_planes = p.out_hi != nullptr;
   for (int c0 = 0; c0 < D; c0 += PASS_COLS) {
     int col[CH];
     bool act[CH];
+    const char* tcol[2][CH];     // per-direction table column bases; inactive lanes are clamped to column 0
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
       col[ch] = c0 + ch * 32 * VEC + lane * VEC;
       act[ch] = col[ch] < D;
+      const int lc = act[ch] ? col[ch] : 0;
+#pragma unroll
+      for (int d = 0; d < 2; ++d)
+        tcol[d][ch] = reinterpret_cast<const char*>(p.dir[d < p.ndir ? d : 0].table) + (size_t)lc * 4;
     }
-    // per-direction table column bases (64-bit) hoisted out of the row loop
-    const char* tcol[2][CH];
+    // 32-bit element offsets of every (direction, instruction, chunk) segment inside an output row
+    int seg[2][NI][CH];
 #pragma unroll
     for (int d = 0; d < 2; ++d)
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
-        tcol[d][ch] = reinterpret_cast<const char*>(p.dir[d < p.ndir ? d : 0].table) + (size_t)col[ch] * 4;
+      for (int j = 0; j < NI; ++j)
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+          seg[d][j][ch] = (int)(d * p.seg_stride_dir + (int64_t)(p.j0 + j) * p.seg_stride_j) + col[ch];
 
     int cur_b = -1;
-    float insr[NI][CH][VEC];
+    float xp[NI][CH][VEC], xn[NI][CH][VEC];   // relu(ins), relu(-ins) of the current question
 #pragma unroll
     for (int j = 0; j < NI; ++j)
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) insr[j][ch][k] = 0.f;
+        for (int k = 0; k < VEC; ++k) xp[j][ch][k] = xn[j][ch][k] = 0.f;
 
-    float* const out_tile = p.out + r0 * p.out_row_stride + p.out_col0;
+    float* const out_tile = to_f32 ? p.out + r0 * p.out_row_stride + p.out_col0 : nullptr;
+    __nv_bfloat16* const hi_tile = to_planes ? p.out_hi + r0 * p.ld_planes + p.out_col0 : nullptr;
+    __nv_bfloat16* const lo_tile = to_planes ? p.out_lo + r0 * p.ld_planes + p.out_col0 : nullptr;
 
     for (int lr = warp; lr < nrows; lr += kWarps) {
       if (MODE == MODE_MSG) {
@@ -249,11 +302,20 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
 #pragma unroll
           for (int j = 0; j < NI; ++j)
 #pragma unroll
-            for (int ch = 0; ch < CH; ++ch)
-              if (act[ch]) ldg_vec<VEC>(insr[j][ch], p.ins + ((int64_t)b * p.I + p.j0 + j) * D + col[ch]);
+            for (int ch = 0; ch < CH; ++ch) {
+              float x[VEC];
+              ldg_vec<VEC>(x, p.ins + ((int64_t)b * p.I + p.j0 + j) * D + (act[ch] ? col[ch] : 0));
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) {
+                xp[j][ch][k] = fmaxf(x[k], 0.f);
+                xn[j][ch][k] = fmaxf(-x[k], 0.f);
+              }
+            }
         }
       }
-      float* const orow = out_tile + (int64_t)lr * p.out_row_stride;
+      float* const orow = to_f32 ? out_tile + (int64_t)lr * p.out_row_stride : nullptr;
+      __nv_bfloat16* const hrow = to_planes ? hi_tile + (int64_t)lr * p.ld_planes : nullptr;
+      __nv_bfloat16* const lrow = to_planes ? lo_tile + (int64_t)lr * p.ld_planes : nullptr;
       float tsum[CH][VEC];   // MODE_TYPE: sum over both directions
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
@@ -283,84 +345,89 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
           if (lane == 0) p.possible[r0 + lr] = cs > 1e-10f ? 1.f : 0.f;
         }
 
+        if (MODE == MODE_MSG && !any) {
+          float z[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) z[k] = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            if (!act[ch]) continue;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+              if (to_f32) st_vec<VEC>(orow + seg[d][j][ch], z);
+              if (to_planes) st_split<VEC>(hrow + seg[d][j][ch], lrow + seg[d][j][ch], z);
+            }
+          }
+          continue;
+        }
+
         float A[CH][VEC], S[CH][VEC];
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
           for (int k = 0; k < VEC; ++k) A[ch][k] = S[ch][k] = 0.f;
 
-        if (any) {
-          int i = beg;
-          for (; i + 4 <= fast_end; i += 4) {
-            int2 m[4];
-            float v[4][CH][VEC];
+        int i = beg;
+        for (; i + 4 <= fast_end; i += 4) {
+          int2 m[4];
+          float v[4][CH][VEC];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) m[u] = s_rc[d][i + u];
+          for (int u = 0; u < 4; ++u) m[u] = s_rc[d][i + u];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 4; ++u)
 #pragma unroll
-              for (int ch = 0; ch < CH; ++ch) {
-                if (act[ch]) {
-                  ldg_vec<VEC>(v[u][ch], tcol[d][ch] + (uint32_t)m[u].x);
-                } else {
+            for (int ch = 0; ch < CH; ++ch) ldg_vec<VEC>(v[u][ch], tcol[d][ch] + (uint32_t)m[u].x);
 #pragma unroll
-                  for (int k = 0; k < VEC; ++k) v[u][ch][k] = 0.f;
-                }
-              }
+          for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int ch = 0; ch < CH; ++ch)
+              accumulate<VEC, MODE>(A[ch], S[ch], v[u][ch], __int_as_float(m[u].y));
+        }
+        for (; i < fast_end; ++i) {
+          const int2 m = s_rc[d][i];
 #pragma unroll
-              for (int ch = 0; ch < CH; ++ch)
-                accumulate<VEC, MODE>(A[ch], S[ch], v[u][ch], __int_as_float(m[u].y));
+          for (int ch = 0; ch < CH; ++ch) {
+            float v[VEC];
+            ldg_vec<VEC>(v, tcol[d][ch] + (uint32_t)m.x);
+            accumulate<VEC, MODE>(A[ch], S[ch], v, __int_as_float(m.y));
           }
-          for (; i < fast_end; ++i) {
-            const int2 m = s_rc[d][i];
+        }
+        for (; i < end; ++i) {   // slow path: the tile's edge slice overflowed the staging buffer (hubs)
+          const int64_t e = ebase + i;
+          const int s = dd.src ? dd.src[e] : 0;
+          const uint32_t off = (uint32_t)dd.rel[e] * (uint32_t)D * 4u;
+          const float c = edge_coeff<MODE>(p, dd, e, s);
 #pragma unroll
-            for (int ch = 0; ch < CH; ++ch) {
-              float v[VEC];
-              if (act[ch]) {
-                ldg_vec<VEC>(v, tcol[d][ch] + (uint32_t)m.x);
-              } else {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) v[k] = 0.f;
-              }
-              accumulate<VEC, MODE>(A[ch], S[ch], v, __int_as_float(m.y));
-            }
-          }
-          for (; i < end; ++i) {   // slow path: the tile's edge slice overflowed the staging buffer (hubs)
-            const int64_t e = ebase + i;
-            const int s = dd.src ? dd.src[e] : 0;
-            const uint32_t off = (uint32_t)dd.rel[e] * (uint32_t)D * 4u;
-            const float c = edge_coeff<MODE>(p, dd, e, s);
-#pragma unroll
-            for (int ch = 0; ch < CH; ++ch) {
-              float v[VEC];
-              if (act[ch]) {
-                ldg_vec<VEC>(v, tcol[d][ch] + off);
-              } else {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) v[k] = 0.f;
-              }
-              accumulate<VEC, MODE>(A[ch], S[ch], v, c);
-            }
+          for (int ch = 0; ch < CH; ++ch) {
+            float v[VEC];
+            ldg_vec<VEC>(v, tcol[d][ch] + off);
+            accumulate<VEC, MODE>(A[ch], S[ch], v, c);
           }
         }
 
         if (MODE == MODE_MSG) {
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch) {
-            if (!act[ch]) continue;
-            float* o = orow + d * p.seg_stride_dir + col[ch];
+            float T[VEC];   // A - S = sum c*relu(-v)
+            if constexpr (VEC % 2 == 0) {
+#pragma unroll
+              for (int k = 0; k < VEC; k += 2) {
+                float2 t2 = __ffma2_rn(make_float2(S[ch][k], S[ch][k + 1]), make_float2(-1.f, -1.f),
+                                       make_float2(A[ch][k], A[ch][k + 1]));
+                T[k] = t2.x; T[k + 1] = t2.y;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) T[k] = A[ch][k] - S[ch][k];
+            }
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
               float y[VEC];
-#pragma unroll
-              for (int k = 0; k < VEC; ++k) {
-                const float x = insr[j][ch][k];
-                const float t = x >= 0.f ? A[ch][k] : A[ch][k] - S[ch][k];   // sum c*relu(+-v)
-                y[k] = fabsf(x) * t;
+              msg_epilogue<VEC>(y, xp[j][ch], xn[j][ch], A[ch], T);
+              if (act[ch]) {
+                if (to_f32) st_vec<VEC>(orow + seg[d][j][ch], y);
+                if (to_planes) st_split<VEC>(hrow + seg[d][j][ch], lrow + seg[d][j][ch], y);
               }
-              st_vec<VEC>(o + (int64_t)(p.j0 + j) * p.seg_stride_j, y);
             }
           }
         } else {
@@ -377,7 +444,8 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
           float y[VEC];
 #pragma unroll
           for (int k = 0; k < VEC; ++k) y[k] = fmaxf(tsum[ch][k], 0.f);
-          st_vec<VEC>(orow + col[ch], y);
+          if (to_f32) st_vec<VEC>(orow + col[ch], y);
+          if (to_planes) st_split<VEC>(hrow + col[ch], lrow + col[ch], y);
         }
       }
     }
@@ -402,7 +470,9 @@ int launch_agg(AggParams p, cudaStream_t stream) {
     size_t a = (size_t)v * 4;
     bool ok = p.D % v == 0 && p.out_row_stride % v == 0 && p.out_col0 % v == 0 &&
               p.seg_stride_j % v == 0 && p.seg_stride_dir % v == 0 &&
-              (reinterpret_cast<size_t>(p.out) % a) == 0 && (reinterpret_cast<size_t>(p.ins) % a) == 0;
+              (reinterpret_cast<size_t>(p.out) % a) == 0 && (reinterpret_cast<size_t>(p.ins) % a) == 0 &&
+              p.ld_planes % v == 0 && (reinterpret_cast<size_t>(p.out_hi) % (a / 2)) == 0 &&
+              (reinterpret_cast<size_t>(p.out_lo) % (a / 2)) == 0;
     for (int d = 0; d < p.ndir; ++d) ok = ok && (reinterpret_cast<size_t>(p.dir[d].table) % a) == 0;
     return ok;
   };
@@ -465,10 +535,13 @@ extern "C" int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, 
                                  const float* w_t, const int32_t* rowptr_h, const int32_t* src_h,
                                  const int32_t* rel_h, const float* w_h, const float* prior,
                                  const float* table_fwd, const float* table_inv, const float* ins,
-                                 float* out, int64_t out_row_stride, int64_t out_col0, int B, int N,
-                                 int D, int I, int64_t F, void* stream_) {
+                                 float* out, int64_t out_row_stride, int64_t out_col0, void* out_hi,
+                                 void* out_lo, int64_t ld_planes, int B, int N, int D, int I, int64_t F,
+                                 void* stream_) {
   using namespace gr;
-  GR_CHECK_ARG(rowptr_t && rowptr_h && prior && table_fwd && table_inv && ins && out, "null pointer");
+  GR_CHECK_ARG(rowptr_t && rowptr_h && prior && table_fwd && table_inv && ins, "null pointer");
+  GR_CHECK_ARG(out || (out_hi && out_lo), "no output requested");
+  GR_CHECK_ARG(!out_hi || (out_lo && ld_planes > 0), "out_lo / ld_planes missing");
   GR_CHECK_ARG(F == 0 || (src_t && rel_t && src_h && rel_h), "null edge arrays");
   GR_CHECK_ARG(B > 0 && N > 0 && D > 0 && I > 0, "B, N, D, I must be positive");
   AggParams p{};
@@ -476,6 +549,8 @@ extern "C" int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, 
   p.dir[1] = AggDir{rowptr_h, src_h, rel_h, w_h, table_inv};
   p.ndir = 2;
   p.prior = prior; p.ins = ins; p.out = out; p.possible = nullptr;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  p.ld_planes = out_hi ? ld_planes : 0;
   p.out_row_stride = out_row_stride; p.out_col0 = out_col0;
   p.seg_stride_j = 2 * (int64_t)D; p.seg_stride_dir = D;
   p.B = B; p.N = N; p.D = D; p.I = I; p.j0 = 0;
@@ -485,10 +560,12 @@ extern "C" int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, 
 
 extern "C" int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, const float* w_t,
                              const int32_t* rowptr_h, const int32_t* rel_h, const float* w_h,
-                             const float* table, float* out, int64_t out_row_stride, int B, int N,
-                             int D, int64_t F, void* stream_) {
+                             const float* table, float* out, int64_t out_row_stride, void* out_hi,
+                             void* out_lo, int64_t ld_planes, int B, int N, int D, int64_t F,
+                             void* stream_) {
   using namespace gr;
-  GR_CHECK_ARG(rowptr_t && rowptr_h && table && out, "null pointer");
+  GR_CHECK_ARG(rowptr_t && rowptr_h && table, "null pointer");
+  GR_CHECK_ARG(out || (out_hi && out_lo), "no output requested");
   GR_CHECK_ARG(F == 0 || (rel_t && rel_h), "null edge arrays");
   GR_CHECK_ARG(B > 0 && N > 0 && D > 0, "B, N, D must be positive");
   AggParams p{};
@@ -496,6 +573,8 @@ extern "C" int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, cons
   p.dir[1] = AggDir{rowptr_h, nullptr, rel_h, w_h, table};
   p.ndir = 2;
   p.prior = nullptr; p.ins = nullptr; p.out = out; p.possible = nullptr;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  p.ld_planes = out_hi ? ld_planes : 0;
   p.out_row_stride = out_row_stride; p.out_col0 = 0;
   p.seg_stride_j = 0; p.seg_stride_dir = 0;
   p.B = B; p.N = N; p.D = D; p.I = 1; p.j0 = 0;

@@ -69,7 +69,7 @@ bool make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int
 // ---------------------------------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int64_t K,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                  int64_t ldo, int vec_ok) {
+                                  int64_t ldo, int vec_ok, int vec_st) {
   const int64_t kq = (K + 3) / 4;
   const int64_t total = M * kq;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -93,7 +93,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ A, int64_t lda, int6
     }
     __nv_bfloat16* ph = hi + m * ldo + k;
     __nv_bfloat16* pl = lo + m * ldo + k;
-    if (k + 3 < ldo) {   // ldo is a multiple of 8: 8-byte aligned stores
+    if (vec_st && k + 3 < ldo) {   // 8-byte aligned plane bases and ldo % 4 == 0
       *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(h);
       *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<uint2*>(l);
     } else {
@@ -172,14 +172,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 struct TcParams {
   const float* bias;
-  float* C;
+  float* C;                 // fp32 output [M, N] (may be null)
   int64_t ldc;
-  int M, N, K, n_pad, stages, tmem_cols;
+  __nv_bfloat16* c_hi;      // optional bf16 hi/lo planes of the output (next layer's A operand)
+  __nv_bfloat16* c_lo;
+  int64_t ldc16;
+  const float* w_score;     // optional: dots[m] = sum_n out[m,n] * w_score[n]   (score_func, reasongnn.py:165)
+  float* dots;
+  int M, N, K, n_pad, stages, num_tiles;
   uint32_t flags;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kAccStride = 256;   // TMEM columns per accumulator buffer (two buffers -> 512 columns)
+
 // ---------------------------------------------------------------------------------------------------
-// the GEMM kernel
+// the GEMM kernel: persistent over 128-row tiles; TMEM accumulators double-buffered so the epilogue of
+// tile i overlaps the TMA/MMA mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -192,13 +204,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const int w_bytes = p.n_pad * BK * 2;       // n_pad * 128
   const int stage_bytes = 2 * a_bytes + 2 * w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* full_bar = bars;                  // [stages]
-  uint64_t* empty_bar = bars + p.stages;      // [stages]
-  uint64_t* tmem_full_bar = bars + 2 * p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  uint64_t* full_bar = bars;                       // [stages]
+  uint64_t* empty_bar = bars + p.stages;           // [stages]
+  uint64_t* tmem_full_bar = bars + 2 * p.stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
   const int nkb = (p.K + BK - 1) / BK;
 
   if (warp == 1 && lane == 0) {
@@ -206,12 +218,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);            // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
-                 "r"((uint32_t)p.tmem_cols)
+                 "r"(2u * kAccStride)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -225,15 +240,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (lane == 0) {
       uint32_t phase = 0;
       int s = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&empty_bar[s], phase ^ 1);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-        tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m0);
-        tma_load_2d(st + a_bytes, &map_a_lo, &full_bar[s], kb * BK, m0);
-        tma_load_2d(st + 2 * a_bytes, &map_w_hi, &full_bar[s], kb * BK, 0);
-        tma_load_2d(st + 2 * a_bytes + w_bytes, &map_w_lo, &full_bar[s], kb * BK, 0);
-        if (++s == p.stages) { s = 0; phase ^= 1; }
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m0);
+          tma_load_2d(st + a_bytes, &map_a_lo, &full_bar[s], kb * BK, m0);
+          tma_load_2d(st + 2 * a_bytes, &map_w_hi, &full_bar[s], kb * BK, 0);
+          tma_load_2d(st + 2 * a_bytes + w_bytes, &map_w_lo, &full_bar[s], kb * BK, 0);
+          if (++s == p.stages) { s = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -243,77 +261,121 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       uint32_t phase = 0;
-      int s = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[s], phase);
+      int s = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t da_hi = make_smem_desc(sa), da_lo = make_smem_desc(sa + a_bytes);
-        const uint64_t dw_hi = make_smem_desc(sa + 2 * a_bytes);
-        const uint64_t dw_lo = make_smem_desc(sa + 2 * a_bytes + w_bytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t da_hi = make_smem_desc(sa), da_lo = make_smem_desc(sa + a_bytes);
+          const uint64_t dw_hi = make_smem_desc(sa + 2 * a_bytes);
+          const uint64_t dw_lo = make_smem_desc(sa + 2 * a_bytes + w_bytes);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
-          umma_bf16(tmem_base, da_hi + adv, dw_hi + adv, idesc, (kb | k) ? 1u : 0u);
-          umma_bf16(tmem_base, da_hi + adv, dw_lo + adv, idesc, 1u);
-          umma_bf16(tmem_base, da_lo + adv, dw_hi + adv, idesc, 1u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
+            umma_bf16(tmem_d, da_hi + adv, dw_hi + adv, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_d, da_hi + adv, dw_lo + adv, idesc, 1u);
+            umma_bf16(tmem_d, da_lo + adv, dw_hi + adv, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);               // frees this smem stage once the MMAs have read it
+          if (++s == p.stages) { s = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[s]);               // frees this smem stage once the MMAs have read it
-        if (++s == p.stages) { s = 0; phase ^= 1; }
+        umma_commit(&tmem_full_bar[acc]);           // accumulator complete -> epilogue
       }
-      umma_commit(tmem_full_bar);                 // accumulator complete -> epilogue
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
-    const int64_t row = (int64_t)m0 + row_in_tile;
     const bool relu = p.flags & GR_LINEAR_RELU;
-    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    float* crow = p.C + row * p.ldc;
-    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (row < p.M) {
-        float v[16];
+    const bool vec_ok = p.C && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec16_ok = p.c_hi && (p.ldc16 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c_hi) & 7) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.c_lo) & 7) == 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = (int64_t)tile * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      float* crow = p.C ? p.C + row * p.ldc : nullptr;
+      float dot = 0.f;
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
+        if (row_ok) {
+          float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          float x = __uint_as_float(r[j]);
-          if (col < p.N) {
-            if (p.bias) x += __ldg(p.bias + col);
-            if (relu) x = fmaxf(x, 0.f);
+          for (int j = 0; j < 16; ++j) {
+            const int col = c0 + j;
+            float x = __uint_as_float(r[j]);
+            if (col < p.N) {
+              if (p.bias) x += __ldg(p.bias + col);
+              if (relu) x = fmaxf(x, 0.f);
+              if (p.w_score) dot = fmaf(x, __ldg(p.w_score + col), dot);
+            }
+            v[j] = x;
           }
-          v[j] = x;
-        }
-        if (vec_ok && c0 + 16 <= p.N) {
+          if (crow) {
+            if (vec_ok && c0 + 16 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.N) crow[c0 + j] = v[j];
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.N) crow[c0 + j] = v[j];
+            }
+          }
+          if (p.c_hi) {
+            __nv_bfloat16 h[16], l[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              h[j] = __float2bfloat16_rn(v[j]);
+              l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+            }
+            __nv_bfloat16* ph = p.c_hi + row * p.ldc16 + c0;
+            __nv_bfloat16* pl = p.c_lo + row * p.ldc16 + c0;
+            if (vec16_ok && c0 + 16 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                *reinterpret_cast<uint2*>(ph + j) = *reinterpret_cast<uint2*>(h + j);
+                *reinterpret_cast<uint2*>(pl + j) = *reinterpret_cast<uint2*>(l + j);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.N) { ph[j] = h[j]; pl[j] = l[j]; }
+            }
+          }
         }
       }
+      if (p.dots && row_ok) p.dots[row] = dot;
+      // release the accumulator to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)p.tmem_cols)
+                 "r"(2u * kAccStride)
                  : "memory");
   }
 }
 
 struct TcPlan {
   int64_t kp;          // plane row stride (elements), multiple of 8
-  int n_pad, stages, tmem_cols;
-  size_t a_plane_bytes, w_plane_bytes, total_bytes, smem_bytes;
+  int n_pad, stages;
+  size_t a_plane_bytes, w_plane_bytes, total_bytes, w_only_bytes, smem_bytes;
   bool ok;
 };
 
@@ -322,18 +384,52 @@ TcPlan plan_tc(int64_t M, int64_t N, int64_t K) {
   t.ok = (N >= 8 && N <= 256 && K >= 8 && M >= 1);
   t.kp = (K + 7) / 8 * 8;
   t.n_pad = (int)((N + 15) / 16 * 16);
-  int cols = 32;
-  while (cols < t.n_pad) cols <<= 1;
-  t.tmem_cols = cols;
   const size_t stage = 2 * (size_t)BM * BK * 2 + 2 * (size_t)t.n_pad * BK * 2;
   int stages = (int)((200 * 1024) / stage);
   t.stages = stages > 6 ? 6 : stages;
   if (t.stages < 2) t.ok = false;
-  t.smem_bytes = (size_t)t.stages * stage + 1024 /*align slack*/ + (2 * t.stages + 2) * 8 + 16;
+  t.smem_bytes = (size_t)t.stages * stage + 1024 /*align slack*/ + (2 * t.stages + 4) * 8 + 16;
   t.a_plane_bytes = align_up((size_t)M * t.kp * 2, 256);
   t.w_plane_bytes = align_up((size_t)N * t.kp * 2, 256);
   t.total_bytes = 2 * t.a_plane_bytes + 2 * t.w_plane_bytes;
+  t.w_only_bytes = 2 * t.w_plane_bytes;
   return t;
+}
+
+int split_launch(const float* A, int64_t lda, int64_t M, int64_t K, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                 int64_t ldo, cudaStream_t stream) {
+  int va = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  int64_t work = M * ((K + 3) / 4);
+  int grid = (int)std::min<int64_t>(ceil_div(work, 256), 32LL * sm_count());
+  int vs = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) &&
+           ((reinterpret_cast<uintptr_t>(lo) & 7) == 0);
+  split_bf16_kernel<<<grid, 256, 0, stream>>>(A, lda, M, K, hi, lo, ldo, va, vs);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
+int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int64_t lda16,
+              const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int64_t ldw16, const TcPlan& t,
+              TcParams p, cudaStream_t stream) {
+  CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
+  if (!make_tmap(&m_a_hi, a_hi, p.M, p.K, lda16, BM) || !make_tmap(&m_a_lo, a_lo, p.M, p.K, lda16, BM) ||
+      !make_tmap(&m_w_hi, w_hi, p.N, p.K, ldw16, t.n_pad) || !make_tmap(&m_w_lo, w_lo, p.N, p.K, ldw16, t.n_pad)) {
+    set_error("gr_linear_tc: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned, row strides "
+              "multiples of 8 elements)");
+    return GR_ERR_CUDA;
+  }
+  p.n_pad = t.n_pad; p.stages = t.stages;
+  p.num_tiles = (int)ceil_div(p.M, BM);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       220 * 1024));
+    attr_set = true;
+  }
+  unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, sm_count());
+  linear_tc_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, p);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
 }
 
 }  // namespace
@@ -347,6 +443,20 @@ bool linear_tc_supported(int64_t M, int64_t N, int64_t K) {
 extern "C" size_t gr_linear_tc_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   return gr::plan_tc(M, N, K).total_bytes;
+}
+
+extern "C" size_t gr_linear_tc_planes_workspace_bytes(int64_t N, int64_t K) {
+  if (N <= 0 || K <= 0) return 0;
+  return gr::plan_tc(1, N, K).w_only_bytes;
+}
+
+extern "C" int gr_split_bf16(const float* A, int64_t lda, int64_t M, int64_t K, void* hi, void* lo,
+                             int64_t ld_out, void* stream_) {
+  using namespace gr;
+  GR_CHECK_ARG(A && hi && lo, "null pointer");
+  GR_CHECK_ARG(M > 0 && K > 0 && lda >= K && ld_out >= K && ld_out % 8 == 0, "bad shape / ld_out % 8 != 0");
+  return split_launch(A, lda, M, K, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo),
+                      ld_out, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
@@ -377,36 +487,51 @@ extern "C" int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t
   __nv_bfloat16* a_lo = reinterpret_cast<__nv_bfloat16*>(ws + t.a_plane_bytes);
   __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(ws + 2 * t.a_plane_bytes);
   __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + 2 * t.a_plane_bytes + t.w_plane_bytes);
-  {
-    int va = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    int64_t work = M * ((K + 3) / 4);
-    int grid = (int)std::min<int64_t>(ceil_div(work, 256), 32LL * sm_count());
-    split_bf16_kernel<<<grid, 256, 0, stream>>>(A, lda, M, K, a_hi, a_lo, t.kp, va);
-    GR_CHECK_LAUNCH();
-    int vw = (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
-    work = N * ((K + 3) / 4);
-    grid = (int)std::min<int64_t>(ceil_div(work, 256), 32LL * sm_count());
-    split_bf16_kernel<<<grid, 256, 0, stream>>>(W, ldw, N, K, w_hi, w_lo, t.kp, vw);
-    GR_CHECK_LAUNCH();
-  }
-  CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
-  if (!make_tmap(&m_a_hi, a_hi, M, K, t.kp, BM) || !make_tmap(&m_a_lo, a_lo, M, K, t.kp, BM) ||
-      !make_tmap(&m_w_hi, w_hi, N, K, t.kp, t.n_pad) || !make_tmap(&m_w_lo, w_lo, N, K, t.kp, t.n_pad)) {
-    set_error("gr_linear_tc: cuTensorMapEncodeTiled failed");
-    return GR_ERR_CUDA;
-  }
+  int rc = split_launch(A, lda, M, K, a_hi, a_lo, t.kp, stream);
+  if (rc != GR_OK) return rc;
+  rc = split_launch(W, ldw, N, K, w_hi, w_lo, t.kp, stream);
+  if (rc != GR_OK) return rc;
   TcParams p{};
   p.bias = bias; p.C = C; p.ldc = ldc;
-  p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.n_pad = t.n_pad; p.stages = t.stages; p.tmem_cols = t.tmem_cols; p.flags = flags;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       220 * 1024));
-    attr_set = true;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.flags = flags;
+  return launch_tc(a_hi, a_lo, t.kp, w_hi, w_lo, t.kp, t, p, stream);
+}
+
+extern "C" int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t lda16, const float* W,
+                                   int64_t ldw, const float* bias, float* C, int64_t ldc, void* C_hi,
+                                   void* C_lo, int64_t ldc16, const float* w_score, float* dots, int64_t M,
+                                   int64_t N, int64_t K, uint32_t flags, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
+  using namespace gr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  GR_CHECK_ARG(A_hi && A_lo && W && workspace, "null pointer");
+  GR_CHECK_ARG(C || C_hi, "no output requested");
+  GR_CHECK_ARG(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
+  GR_CHECK_ARG(lda16 >= K && lda16 % 8 == 0 && ldw >= K, "lda16 must be >= K and a multiple of 8");
+  GR_CHECK_ARG(!C || ldc >= N, "ldc smaller than N");
+  GR_CHECK_ARG(!C_hi || (C_lo && ldc16 >= N), "C_lo missing or ldc16 smaller than N");
+  GR_CHECK_ARG(!dots || w_score, "dots requested without w_score");
+  GR_CHECK_ARG(M < (int64_t)0x7fffffff - BM, "M exceeds int32 range");
+  TcPlan t = plan_tc(M, N, K);
+  if (!t.ok) {
+    set_error("gr_linear_tc_planes: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N,
+              (long long)K);
+    return GR_ERR_UNSUPPORTED;
   }
-  unsigned grid = (unsigned)ceil_div(M, BM);
-  linear_tc_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, p);
-  GR_CHECK_LAUNCH();
-  return GR_OK;
+  if (workspace_bytes < t.w_only_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("gr_linear_tc_planes: workspace too small or not 256-byte aligned");
+    return GR_ERR_WORKSPACE;
+  }
+  char* ws = reinterpret_cast<char*>(workspace);
+  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + t.w_plane_bytes);
+  int rc = split_launch(W, ldw, N, K, w_hi, w_lo, t.kp, stream);
+  if (rc != GR_OK) return rc;
+  TcParams p{};
+  p.bias = bias; p.C = C; p.ldc = ldc;
+  p.c_hi = reinterpret_cast<__nv_bfloat16*>(C_hi); p.c_lo = reinterpret_cast<__nv_bfloat16*>(C_lo);
+  p.ldc16 = ldc16; p.w_score = w_score; p.dots = dots;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.flags = flags;
+  return launch_tc(reinterpret_cast<const __nv_bfloat16*>(A_hi), reinterpret_cast<const __nv_bfloat16*>(A_lo),
+                   lda16, w_hi, w_lo, t.kp, t, p, stream);
 }

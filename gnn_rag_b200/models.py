@@ -113,12 +113,18 @@ class BaseModel(nn.Module):
                 "LSTM question encoder only" % args["lm"])
         return LSTMInstruction(args, self.word_embedding, self.num_word)
 
-    def _get_ent_init(self, db, rel_features, out):                # rearev.py:79-88 / nsm.py:84-94
+    def _get_ent_init(self, db, rel_features, layer):              # rearev.py:79-88 / nsm.py:84-94
+        """Initial node embeddings, written straight into the reasoning layer's h slot(s)."""
+        out, planes = layer.h_view, layer.cur_planes()
+        if planes is not None:
+            planes = tuple(p[:, : self.entity_dim] for p in planes)
         if self.encode_type:
-            self.type_layer(db.graph, rel_features, out)
+            self.type_layer(db.graph, rel_features, out, planes)
         else:
             emb = self.entity_embedding(db.local_entity).view(db.B * db.N, -1).contiguous()
             ops.linear(emb, self.entity_linear.weight, self.entity_linear.bias, out=out)
+            if planes is not None:
+                ops.split_bf16(out, planes[0], planes[1])
         return out
 
     # base_model.py:186-215 + rearev.py:156-160
@@ -192,7 +198,7 @@ class ReaRev(BaseModel):
         B, N = db.B, db.N
         rel_f, rel_f_inv = self.get_rel_feature()
         self.reasoning.init_reason(db, rel_f, rel_f_inv)
-        self._get_ent_init(db, rel_f, self.reasoning.h_view)    # TypeLayer straight into X[:, :D]
+        self._get_ent_init(db, rel_f, self.reasoning)           # TypeLayer straight into the h slot
         instructions = self.instruction(db.q_input)              # rearev.py:192-196
         self.dist_history = [db.seed_dist]
         h = self.reasoning.h_view
@@ -250,7 +256,7 @@ class NSM(BaseModel):
         self.last_batch = db
         rel_f = self.get_rel_feature()
         self.reasoning.init_reason(db, rel_f)
-        self._get_ent_init(db, rel_f, self.reasoning.h_view)
+        self._get_ent_init(db, rel_f, self.reasoning)
         instruction_list = self.instruction(db.q_input)
         dist = db.seed_dist
         self.dist_history = [dist]

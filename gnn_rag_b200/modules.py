@@ -32,10 +32,10 @@ class TypeLayer(nn.Module):
         self.device = device
         self.norm_rel = norm_rel
 
-    def forward(self, graph, rel_features, out):
+    def forward(self, graph, rel_features, out, planes=None):
         table = ops.linear(rel_features, self.kb_self_linear.weight, self.kb_self_linear.bias)
         wt, wh = (graph.wr_t, graph.wr_h) if self.norm_rel else (None, None)
-        ops.type_layer(graph, table, out, wt, wh)
+        ops.type_layer(graph, table, out, wt, wh, planes=planes)
         return out
 
 
@@ -139,18 +139,51 @@ class LSTMInstruction(nn.Module):
 
 
 class _GraphLayerBase(nn.Module):
-    """State shared by the two reasoning layers: activation ping-pong buffers X[2] of shape [B*N, Kd]
-    whose first D columns hold the node embeddings h and whose remaining columns receive the aggregated
-    neighbour messages -- the ``torch.cat`` of reasongnn.py:158-161 / nsm_gnn.py:62 is never materialised
-    by a copy, the aggregation kernel writes straight into its slot."""
+    """State shared by the two reasoning layers: the layer-input activation matrix [B*N, Kd] whose first D
+    columns hold the node embeddings h and whose remaining columns receive the aggregated neighbour
+    messages -- the ``torch.cat`` of reasongnn.py:158-161 / nsm_gnn.py:62 is never materialised by a copy,
+    the aggregation kernel writes straight into its slot.  Two storage modes:
+
+      planes (default): the matrix is kept as split-bf16 hi/lo planes (hi + lo = value to 2^-18), which is
+          the A-operand layout of the tcgen05 e2e GEMM; h additionally lives in fp32 ``h32`` [B*N, D].
+      fp32: ping-pong fp32 buffers X[2] feeding the exact-fp32 SIMT linear (ops.TC_LINEAR = False)."""
 
     def _alloc(self, Nt, Kd, device):
-        self.X = [torch.empty(Nt, Kd, dtype=torch.float32, device=device) for _ in range(2)]
+        D = self.entity_dim
+        self.use_planes = bool(ops.TC_LINEAR) and 8 <= D <= 256
         self.cur = 0
+        self.Kd = Kd
+        if self.use_planes:
+            Kp = (Kd + 7) // 8 * 8
+            self.P = [[torch.empty(Nt, Kp, dtype=torch.bfloat16, device=device) for _ in range(2)]
+                      for _ in range(2)]
+            self.h32 = torch.empty(Nt, D, dtype=torch.float32, device=device)
+            self.dots = torch.empty(Nt, dtype=torch.float32, device=device)
+        else:
+            self.X = [torch.empty(Nt, Kd, dtype=torch.float32, device=device) for _ in range(2)]
 
     @property
     def h_view(self):
-        return self.X[self.cur][:, : self.entity_dim]
+        return self.h32 if self.use_planes else self.X[self.cur][:, : self.entity_dim]
+
+    def cur_planes(self):
+        return tuple(self.P[self.cur]) if self.use_planes else None
+
+    def _e2e_and_score(self, e2e, mask):
+        """h <- relu(e2e([h, nb...])); dist = softmax(score_func(h) + mask)."""
+        D = self.entity_dim
+        sw, sb = self.score_func.weight.view(-1), self.score_func.bias
+        if self.use_planes:
+            hi, lo = self.P[self.cur]
+            nhi, nlo = self.P[1 - self.cur]
+            ops.linear_tc_planes(hi, lo, self.Kd, e2e.weight, e2e.bias, out=self.h32, out_planes=(nhi, nlo),
+                                 w_score=sw, dots=self.dots, relu=True)
+            self.cur = 1 - self.cur
+            return ops.masked_softmax(self.dots, sb, mask, self.B, self.N)
+        X, Xn = self.X[self.cur], self.X[1 - self.cur]
+        ops.e2e_linear(X, e2e.weight, e2e.bias, Xn[:, :D])
+        self.cur = 1 - self.cur
+        return ops.score_softmax(self.h_view, sw, sb, mask, self.B, self.N)
 
 
 class ReasonGNNLayer(_GraphLayerBase):
@@ -197,15 +230,12 @@ class ReasonGNNLayer(_GraphLayerBase):
         concat slots, h <- relu(e2e_k([h, nb...])), score, masked softmax."""
         D = self.entity_dim
         g = self.graph
-        X, Xn = self.X[self.cur], self.X[1 - self.cur]
         tf, ti = self.tables[step]
         wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
-        ops.aggregate_dual(g, current_dist, tf, ti, relational_ins, X, D, wt, wh)
-        e2e = getattr(self, "e2e_linear" + str(step))
-        ops.e2e_linear(X, e2e.weight, e2e.bias, Xn[:, :D])
-        self.cur = 1 - self.cur
-        dist = ops.score_softmax(self.h_view, self.score_func.weight.view(-1), self.score_func.bias,
-                                 self.local_entity_mask, self.B, self.N)
+        ops.aggregate_dual(g, current_dist, tf, ti, relational_ins,
+                           None if self.use_planes else self.X[self.cur], D, wt, wh,
+                           planes=self.cur_planes())
+        dist = self._e2e_and_score(getattr(self, "e2e_linear" + str(step)), self.local_entity_mask)
         return dist, self.h_view
 
 
@@ -234,18 +264,22 @@ class NSMLayer(_GraphLayerBase):
             lin = getattr(self, "rel_linear" + str(k))
             self.tables.append(ops.linear(rel_features, lin.weight, lin.bias))
         self.possible = torch.empty(db.B * db.N, dtype=torch.float32, device=db.local_entity.device)
+        if self.use_planes:
+            self.nb32 = torch.empty(db.B * db.N, D, dtype=torch.float32, device=db.local_entity.device)
 
     def forward(self, current_dist, relational_ins, step=0):
         """nsm_gnn.py:54-77 + :87-112 (forward direction only, e2e: 2D -> D)."""
         D = self.entity_dim
         g = self.graph
-        X, Xn = self.X[self.cur], self.X[1 - self.cur]
         w = g.w_t if self.normalized_gnn else None
-        ops.aggregate(g, "fwd", current_dist, self.tables[step], relational_ins.view(self.B, 1, D),
-                      out=X, out_col0=D, seg_stride=D, w=w, possible=self.possible)
-        e2e = getattr(self, "e2e_linear" + str(step))
-        ops.e2e_linear(X, e2e.weight, e2e.bias, Xn[:, :D])
-        self.cur = 1 - self.cur
+        if self.use_planes:
+            # single-direction aggregate writes fp32; split into the planes' neighbour slot
+            ops.aggregate(g, "fwd", current_dist, self.tables[step], relational_ins.view(self.B, 1, D),
+                          out=self.nb32, out_col0=0, seg_stride=D, w=w, possible=self.possible)
+            hi, lo = self.P[self.cur]
+            ops.split_bf16(self.nb32, hi[:, D:], lo[:, D:])
+        else:
+            ops.aggregate(g, "fwd", current_dist, self.tables[step], relational_ins.view(self.B, 1, D),
+                          out=self.X[self.cur], out_col0=D, seg_stride=D, w=w, possible=self.possible)
         mask = self.local_entity_mask * self.possible if self.reason_kb else self.local_entity_mask
-        return ops.score_softmax(self.h_view, self.score_func.weight.view(-1), self.score_func.bias,
-                                 mask, self.B, self.N)
+        return self._e2e_and_score(getattr(self, "e2e_linear" + str(step)), mask)

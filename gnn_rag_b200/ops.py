@@ -210,32 +210,81 @@ def aggregate(g, direction, prior, table, ins, out=None, out_col0=0, seg_stride=
     return out
 
 
-def aggregate_dual(g, prior, table_fwd, table_inv, ins, out, out_col0, w_t=None, w_h=None):
-    """Both directions of one ReaRev layer: out[:, out_col0 + (2j+dir)*D : +D] (reasongnn.py:150-161)."""
+def aggregate_dual(g, prior, table_fwd, table_inv, ins, out, out_col0, w_t=None, w_h=None, planes=None):
+    """Both directions of one ReaRev layer: out[:, out_col0 + (2j+dir)*D : +D] (reasongnn.py:150-161).
+    ``planes`` = (hi, lo) bf16 [B*N, ld] tensors: write the split-bf16 A-operand planes (``out`` may be
+    None)."""
     prior = _cuda(prior, torch.float32, "prior").contiguous()
     ins = _cuda(ins, torch.float32, "ins").contiguous()
     B, I, D = ins.shape
-    assert out.stride(1) == 1 and table_fwd.is_contiguous() and table_inv.is_contiguous()
+    assert table_fwd.is_contiguous() and table_inv.is_contiguous()
+    assert out is None or out.stride(1) == 1
+    hi, lo = planes if planes is not None else (None, None)
     with _AggTimer(("dual", I)):
         rc = _L().gr_aggregate_dual(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t),
                                     _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(w_h),
                                     _p(prior), _p(table_fwd), _p(table_inv), _p(ins), _p(out),
-                                    out.stride(0), out_col0, B, g.N, D, I, g.F, _stream())
+                                    out.stride(0) if out is not None else 0, out_col0,
+                                    _p(hi), _p(lo), hi.stride(0) if hi is not None else 0,
+                                    B, g.N, D, I, g.F, _stream())
     _lib.check(rc)
     STATS.launches += (I + 3) // 4
     return out
 
 
-def type_layer(g, table, out, w_t=None, w_h=None):
-    """out[:, :D] = relu(sum_tail w*table[rel] + sum_head w*table[rel]) (layer_init.py:46-57)."""
+def type_layer(g, table, out, w_t=None, w_h=None, planes=None):
+    """out[:, :D] = relu(sum_tail w*table[rel] + sum_head w*table[rel]) (layer_init.py:46-57); optional
+    split-bf16 planes of the same values."""
     table = _cuda(table, torch.float32, "table").contiguous()
     D = table.shape[1]
-    assert out.stride(1) == 1
+    assert out is None or out.stride(1) == 1
+    hi, lo = planes if planes is not None else (None, None)
     rc = _L().gr_type_layer(_p(g.rowptr_t), _p(g.rel_t), _p(w_t), _p(g.rowptr_h), _p(g.rel_h), _p(w_h),
-                            _p(table), _p(out), out.stride(0), g.B, g.N, D, g.F, _stream())
+                            _p(table), _p(out), out.stride(0) if out is not None else 0,
+                            _p(hi), _p(lo), hi.stride(0) if hi is not None else 0,
+                            g.B, g.N, D, g.F, _stream())
     _lib.check(rc)
     STATS.launches += 1
     return out
+
+
+def split_bf16(A, hi, lo):
+    """fp32 [M,K] -> bf16 hi/lo planes (first K columns of hi/lo)."""
+    A = _cuda(A, torch.float32, "A")
+    M, K = A.shape
+    assert A.stride(1) == 1 and hi.stride(1) == 1 and hi.stride(0) == lo.stride(0)
+    _lib.check(_L().gr_split_bf16(_p(A), A.stride(0), M, K, _p(hi), _p(lo), hi.stride(0), _stream()))
+    STATS.launches += 1
+
+
+def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=None, dots=None, relu=True):
+    """tcgen05 split-bf16 GEMM whose A operand already lives in bf16 hi/lo planes [M, >=K].
+    Writes any of: fp32 ``out`` [M,N]; ``out_planes`` (hi, lo) [M, >=N] (next layer's h columns);
+    ``dots`` [M] = out @ w_score."""
+    M = a_hi.shape[0]
+    N = W.shape[0]
+    assert a_hi.dtype == torch.bfloat16 and a_hi.stride(1) == 1 and a_hi.stride(0) == a_lo.stride(0)
+    assert W.shape[1] == K and W.stride(1) == 1
+    L = _L()
+    nbytes = L.gr_linear_tc_planes_workspace_bytes(N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=a_hi.device)
+    chi, clo = out_planes if out_planes is not None else (None, None)
+    rc = L.gr_linear_tc_planes(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(W), W.stride(0), _p(bias),
+                               _p(out), out.stride(0) if out is not None else 0,
+                               _p(chi), _p(clo), chi.stride(0) if chi is not None else 0,
+                               _p(w_score), _p(dots), M, N, K, LINEAR_RELU if relu else 0,
+                               _p(ws), nbytes, _stream())
+    _lib.check(rc)
+    STATS.launches += 2
+    return out
+
+
+def masked_softmax(dots, b_score, mask, B, N):
+    """dist[b,:] = softmax(dots[b,:] + b + (1-mask)*VERY_NEG)  (reasongnn.py:168-169)."""
+    dist = torch.empty(B, N, dtype=torch.float32, device=dots.device)
+    _lib.check(_L().gr_masked_softmax(_p(dots), _p(b_score), _p(mask.contiguous()), _p(dist), B, N, _stream()))
+    STATS.launches += 2
+    return dist
 
 
 def score_softmax(h, w_score, b_score, mask, B, N, logits_out=None):

@@ -96,6 +96,20 @@ size_t gr_linear_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                  float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, uint32_t flags,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* Same GEMM with the A operand already in split-bf16 planes (written by gr_aggregate_dual / gr_type_layer /
+ * a previous call): no conversion pass over A.  Outputs (each optional, at least one): fp32 C; bf16 planes
+ * C_hi/C_lo (row stride ldc16) = the node-embedding columns of the NEXT layer's A operand; and
+ * dots[m] = sum_n C[m,n] * w_score[n], the score_func dot product (reasongnn.py:165) fused into the
+ * epilogue.  Persistent kernel, TMEM accumulators double-buffered (epilogue overlaps the next tile).
+ * Workspace: gr_linear_tc_planes_workspace_bytes(N, K) (the W planes), 256-byte aligned. */
+size_t gr_linear_tc_planes_workspace_bytes(int64_t N, int64_t K);
+int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t lda16, const float* W, int64_t ldw,
+                        const float* bias, float* C, int64_t ldc, void* C_hi, void* C_lo, int64_t ldc16,
+                        const float* w_score, float* dots, int64_t M, int64_t N, int64_t K,
+                        uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+/* fp32 [M,K] (row stride lda) -> bf16 hi/lo planes (row stride ld_out, multiple of 8). */
+int gr_split_bf16(const float* A, int64_t lda, int64_t M, int64_t K, void* hi, void* lo, int64_t ld_out,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * The aggregation kernel family.
@@ -114,6 +128,12 @@ int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const
  *     inverse  (head CSR, table_inv) -> columns out_col0 + (2j+1)*D
  * which is the concat order of ReasonGNNLayer.forward (reasongnn.py:150-161).
  *
+ * Split-bf16 planes (optional, gr_aggregate_dual / gr_type_layer): when out_hi/out_lo are non-NULL the
+ * result is ALSO (or, with out == NULL, only) written as two bf16 matrices with row stride ld_planes and
+ * the same column indexing as `out`: hi = bf16(y), lo = bf16(y - hi), so hi + lo = y to 2^-18 relative.
+ * That is the A-operand layout gr_linear_tc_planes consumes, so the fp32 concat buffer of
+ * reasongnn.py:158-161 never has to exist.
+ *
  * gr_type_layer: out[n,:] = relu( sum_{tail CSR} w_e table[rel_e] + sum_{head CSR} w_e table[rel_e] ),
  * TypeLayer.forward (layer_init.py:46-57) with table = kb_self_linear(rel_features).
  */
@@ -127,11 +147,13 @@ int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, const int32
                       const int32_t* rel_h, const float* w_h, const float* prior,
                       const float* table_fwd, const float* table_inv, const float* ins,
                       float* out, int64_t out_row_stride, int64_t out_col0,
+                      void* out_hi, void* out_lo, int64_t ld_planes,
                       int B, int N, int D, int I, int64_t F, void* stream);
 
 int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, const float* w_t,
                   const int32_t* rowptr_h, const int32_t* rel_h, const float* w_h,
                   const float* table, float* out, int64_t out_row_stride,
+                  void* out_hi, void* out_lo, int64_t ld_planes,
                   int B, int N, int D, int64_t F, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -143,6 +165,9 @@ int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, const float* w_
 int gr_score_softmax(const float* h, int64_t ldh, const float* w_score, const float* b_score,
                      const float* mask, float* dist, float* logits_out, int B, int N, int D,
                      void* stream);
+/* Same, starting from precomputed dots[b,n] = dot(h[b,n,:], w_score) (gr_linear_tc_planes epilogue). */
+int gr_masked_softmax(const float* dots, const float* b_score, const float* mask, float* dist,
+                      int B, int N, void* stream);
 
 /* seed_retrieve[b,:] = sum_n seed_info[b,n] * h[b,n,:]  (torch.bmm in QueryReform.forward,
  * gnn/modules/query_update.py:40); only rows with seed_info != 0 are read, in index order. */
