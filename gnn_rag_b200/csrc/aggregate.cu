@@ -90,24 +90,45 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-// y -> (hi, lo) bf16 pair per element, hi = bf16(y), lo = bf16(y - hi); vector store of VEC elements each
+// y -> (hi, lo) bf16 pair per element, hi = bf16(y), lo = bf16(y - hi), with packed conversions
+// (cvt.rn.bf16x2.f32); the caller predicates the store.
 template <int VEC>
-__device__ __forceinline__ void st_split(__nv_bfloat16* ph, __nv_bfloat16* pl, const float (&y)[VEC]) {
-  __align__(8) __nv_bfloat16 h[VEC], l[VEC];
+struct SplitVec {
+  uint32_t h[(VEC + 1) / 2], l[(VEC + 1) / 2];
+};
+
+template <int VEC>
+__device__ __forceinline__ SplitVec<VEC> split_vec(const float (&y)[VEC]) {
+  SplitVec<VEC> r;
+  if constexpr (VEC % 2 == 0) {
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    h[k] = __float2bfloat16_rn(y[k]);
-    l[k] = __float2bfloat16_rn(y[k] - __bfloat162float(h[k]));
-  }
-  if (VEC == 4) {
-    *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<const uint2*>(l);
-  } else if (VEC == 2) {
-    *reinterpret_cast<uint32_t*>(ph) = *reinterpret_cast<const uint32_t*>(h);
-    *reinterpret_cast<uint32_t*>(pl) = *reinterpret_cast<const uint32_t*>(l);
+    for (int k = 0; k < VEC; k += 2) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[k], y[k + 1]);
+      const float2 hf = __bfloat1622float2(h2);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(y[k] - hf.x, y[k + 1] - hf.y);
+      r.h[k / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+      r.l[k / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
   } else {
-    ph[0] = h[0];
-    pl[0] = l[0];
+    const __nv_bfloat16 h = __float2bfloat16_rn(y[0]);
+    const __nv_bfloat16 l = __float2bfloat16_rn(y[0] - __bfloat162float(h));
+    r.h[0] = *reinterpret_cast<const unsigned short*>(&h);
+    r.l[0] = *reinterpret_cast<const unsigned short*>(&l);
+  }
+  return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_split(__nv_bfloat16* ph, __nv_bfloat16* pl, const SplitVec<VEC>& r) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<uint2*>(ph) = make_uint2(r.h[0], r.h[1]);
+    *reinterpret_cast<uint2*>(pl) = make_uint2(r.l[0], r.l[1]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<uint32_t*>(ph) = r.h[0];
+    *reinterpret_cast<uint32_t*>(pl) = r.l[0];
+  } else {
+    *reinterpret_cast<unsigned short*>(ph) = (unsigned short)r.h[0];
+    *reinterpret_cast<unsigned short*>(pl) = (unsigned short)r.l[0];
   }
 }
 
@@ -167,7 +188,8 @@ __device__ __forceinline__ void msg_epilogue(float (&y)[VEC], const float (&xp)[
 }
 
 // CH = feature chunks per lane (1 or 2): one pass covers 32*VEC*CH columns.
-template <int VEC, int CH, int NI, int MODE, bool USE_TMA>
+// PLANES: output goes to the split-bf16 planes (p.out_hi/p.out_lo) instead of fp32 p.out.
+template <int VEC, int CH, int NI, int MODE, bool USE_TMA, bool PLANES>
 __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
   __shared__ int32_t s_rowptr[2][kRows + 1];
   __shared__ int2 s_rc[2][kEdgeCap];                       // {table byte offset rel*D*4, float_as_int(c)}
@@ -256,29 +278,27 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
 
   // ---------------- phase 2: one warp per destination row, lanes across features ----------------------
   constexpr int PASS_COLS = 32 * VEC * CH;
-  const bool to_f32 = p.out != nullptr, to_planes = p.out_hi != nullptr;
+  constexpr int CHW = 32 * VEC;                       // columns per chunk
+  const int64_t ld = PLANES ? p.ld_planes : p.out_row_stride;
   for (int c0 = 0; c0 < D; c0 += PASS_COLS) {
-    int col[CH];
+    const int col0 = c0 + lane * VEC;                 // this lane's column in chunk 0
     bool act[CH];
     const char* tcol[2][CH];     // per-direction table column bases; inactive lanes are clamped to column 0
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
-      col[ch] = c0 + ch * 32 * VEC + lane * VEC;
-      act[ch] = col[ch] < D;
-      const int lc = act[ch] ? col[ch] : 0;
+      act[ch] = col0 + ch * CHW < D;
+      const int lc = act[ch] ? col0 + ch * CHW : 0;
 #pragma unroll
       for (int d = 0; d < 2; ++d)
         tcol[d][ch] = reinterpret_cast<const char*>(p.dir[d < p.ndir ? d : 0].table) + (size_t)lc * 4;
     }
-    // 32-bit element offsets of every (direction, instruction, chunk) segment inside an output row
-    int seg[2][NI][CH];
+    // warp-uniform element offsets of every (direction, instruction) segment inside an output row
+    int seg[2][NI];
 #pragma unroll
     for (int d = 0; d < 2; ++d)
 #pragma unroll
       for (int j = 0; j < NI; ++j)
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-          seg[d][j][ch] = (int)(d * p.seg_stride_dir + (int64_t)(p.j0 + j) * p.seg_stride_j) + col[ch];
+        seg[d][j] = (int)(d * p.seg_stride_dir + (int64_t)(p.j0 + j) * p.seg_stride_j);
 
     int cur_b = -1;
     float xp[NI][CH][VEC], xn[NI][CH][VEC];   // relu(ins), relu(-ins) of the current question
@@ -289,9 +309,10 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) xp[j][ch][k] = xn[j][ch][k] = 0.f;
 
-    float* const out_tile = to_f32 ? p.out + r0 * p.out_row_stride + p.out_col0 : nullptr;
-    __nv_bfloat16* const hi_tile = to_planes ? p.out_hi + r0 * p.ld_planes + p.out_col0 : nullptr;
-    __nv_bfloat16* const lo_tile = to_planes ? p.out_lo + r0 * p.ld_planes + p.out_col0 : nullptr;
+    // per-lane base pointers of the tile (row 0, this lane's chunk-0 column)
+    float* const out_lane = PLANES ? nullptr : p.out + r0 * ld + p.out_col0 + col0;
+    __nv_bfloat16* const hi_lane = PLANES ? p.out_hi + r0 * ld + p.out_col0 + col0 : nullptr;
+    __nv_bfloat16* const lo_lane = PLANES ? p.out_lo + r0 * ld + p.out_col0 + col0 : nullptr;
 
     for (int lr = warp; lr < nrows; lr += kWarps) {
       if (MODE == MODE_MSG) {
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
 #pragma unroll
             for (int ch = 0; ch < CH; ++ch) {
               float x[VEC];
-              ldg_vec<VEC>(x, p.ins + ((int64_t)b * p.I + p.j0 + j) * D + (act[ch] ? col[ch] : 0));
+              ldg_vec<VEC>(x, p.ins + ((int64_t)b * p.I + p.j0 + j) * D + (act[ch] ? col0 + ch * CHW : 0));
 #pragma unroll
               for (int k = 0; k < VEC; ++k) {
                 xp[j][ch][k] = fmaxf(x[k], 0.f);
@@ -313,9 +334,18 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
             }
         }
       }
-      float* const orow = to_f32 ? out_tile + (int64_t)lr * p.out_row_stride : nullptr;
-      __nv_bfloat16* const hrow = to_planes ? hi_tile + (int64_t)lr * p.ld_planes : nullptr;
-      __nv_bfloat16* const lrow = to_planes ? lo_tile + (int64_t)lr * p.ld_planes : nullptr;
+      const int64_t rowoff = (int64_t)lr * ld;        // warp-uniform
+      float* const orow = PLANES ? nullptr : out_lane + rowoff;
+      __nv_bfloat16* const hrow = PLANES ? hi_lane + rowoff : nullptr;
+      __nv_bfloat16* const lrow = PLANES ? lo_lane + rowoff : nullptr;
+      auto store = [&](int off, bool pred, const float (&y)[VEC]) {   // off: warp-uniform element offset
+        if constexpr (PLANES) {
+          const SplitVec<VEC> sv = split_vec<VEC>(y);
+          if (pred) st_split<VEC>(hrow + off, lrow + off, sv);
+        } else {
+          if (pred) st_vec<VEC>(orow + off, y);
+        }
+      };
       float tsum[CH][VEC];   // MODE_TYPE: sum over both directions
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
@@ -350,14 +380,9 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
 #pragma unroll
           for (int k = 0; k < VEC; ++k) z[k] = 0.f;
 #pragma unroll
-          for (int ch = 0; ch < CH; ++ch) {
-            if (!act[ch]) continue;
+          for (int j = 0; j < NI; ++j)
 #pragma unroll
-            for (int j = 0; j < NI; ++j) {
-              if (to_f32) st_vec<VEC>(orow + seg[d][j][ch], z);
-              if (to_planes) st_split<VEC>(hrow + seg[d][j][ch], lrow + seg[d][j][ch], z);
-            }
-          }
+            for (int ch = 0; ch < CH; ++ch) store(seg[d][j] + ch * CHW, act[ch], z);
           continue;
         }
 
@@ -424,10 +449,7 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
             for (int j = 0; j < NI; ++j) {
               float y[VEC];
               msg_epilogue<VEC>(y, xp[j][ch], xn[j][ch], A[ch], T);
-              if (act[ch]) {
-                if (to_f32) st_vec<VEC>(orow + seg[d][j][ch], y);
-                if (to_planes) st_split<VEC>(hrow + seg[d][j][ch], lrow + seg[d][j][ch], y);
-              }
+              store(seg[d][j] + ch * CHW, act[ch], y);
             }
           }
         } else {
@@ -440,12 +462,10 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
       if (MODE == MODE_TYPE) {
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) {
-          if (!act[ch]) continue;
           float y[VEC];
 #pragma unroll
           for (int k = 0; k < VEC; ++k) y[k] = fmaxf(tsum[ch][k], 0.f);
-          if (to_f32) st_vec<VEC>(orow + col[ch], y);
-          if (to_planes) st_split<VEC>(hrow + col[ch], lrow + col[ch], y);
+          store(ch * CHW, act[ch], y);
         }
       }
     }
@@ -455,11 +475,20 @@ __global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
 template <int VEC, int CH, int NI, int MODE>
 int launch_agg2(const AggParams& p, bool tma, cudaStream_t stream) {
   unsigned grid = (unsigned)ceil_div(p.Nt, kRows);
-  if (tma)
-    agg_kernel<VEC, CH, NI, MODE, true><<<grid, kThreads, 0, stream>>>(p);
-  else
-    agg_kernel<VEC, CH, NI, MODE, false><<<grid, kThreads, 0, stream>>>(p);
-  GR_CHECK_LAUNCH();
+  if (p.out) {
+    if (tma)
+      agg_kernel<VEC, CH, NI, MODE, true, false><<<grid, kThreads, 0, stream>>>(p);
+    else
+      agg_kernel<VEC, CH, NI, MODE, false, false><<<grid, kThreads, 0, stream>>>(p);
+    GR_CHECK_LAUNCH();
+  }
+  if (p.out_hi) {   // split-bf16 planes (a second launch only if the caller asked for both formats)
+    if (tma)
+      agg_kernel<VEC, CH, NI, MODE, true, true><<<grid, kThreads, 0, stream>>>(p);
+    else
+      agg_kernel<VEC, CH, NI, MODE, false, true><<<grid, kThreads, 0, stream>>>(p);
+    GR_CHECK_LAUNCH();
+  }
   return GR_OK;
 }
 

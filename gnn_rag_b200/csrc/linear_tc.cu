@@ -22,6 +22,7 @@
 namespace gr {
 
 int g_opt_linear_tc = 0;   // gr_set_option("linear_tc", 0|1): route e2e linears through this kernel
+int g_tc_cluster = 2;      // gr_set_option("tc_cluster", 1|2): CTAs per cluster sharing W tiles by TMA multicast
 
 namespace {
 
@@ -137,6 +138,23 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                               int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 // K-major, 128B-swizzled operand tile: 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -160,6 +178,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -193,6 +218,7 @@ constexpr int kAccStride = 256;   // TMEM columns per accumulator buffer (two bu
 // the GEMM kernel: persistent over 128-row tiles; TMEM accumulators double-buffered so the epilogue of
 // tile i overlaps the TMA/MMA mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------------
+template <int CS>   // cluster size: the CS CTAs of a cluster each load 1/CS of the W tile and multicast it
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -212,11 +238,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + BK - 1) / BK;
+  const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int ncluster = gridDim.x / CS, cid = blockIdx.x / CS;
+  const int ngroups = (p.num_tiles + CS - 1) / CS;       // tile groups: CS consecutive 128-row tiles
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CS);                      // every CTA of the cluster must release the slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -232,6 +262,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CS > 1) cluster_sync_all();                        // all barriers of the cluster are initialised
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -240,16 +271,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (lane == 0) {
       uint32_t phase = 0;
       int s = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = tile * BM;
+      const int w_rows = p.n_pad / CS;                   // W rows this CTA fetches (and multicasts)
+      const int w_slice = w_rows * BK * 2;               // bytes
+      for (int g = cid; g < ngroups; g += ncluster) {
+        const int m0 = (g * CS + crank) * BM;            // may lie beyond M for the last group: zero-filled
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           uint8_t* st = smem + (size_t)s * stage_bytes;
           mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m0);
           tma_load_2d(st + a_bytes, &map_a_lo, &full_bar[s], kb * BK, m0);
-          tma_load_2d(st + 2 * a_bytes, &map_w_hi, &full_bar[s], kb * BK, 0);
-          tma_load_2d(st + 2 * a_bytes + w_bytes, &map_w_lo, &full_bar[s], kb * BK, 0);
+          if (CS == 1) {
+            tma_load_2d(st + 2 * a_bytes, &map_w_hi, &full_bar[s], kb * BK, 0);
+            tma_load_2d(st + 2 * a_bytes + w_bytes, &map_w_lo, &full_bar[s], kb * BK, 0);
+          } else {
+            tma_load_2d_mc(st + 2 * a_bytes + crank * w_slice, &map_w_hi, &full_bar[s], kb * BK,
+                           crank * w_rows, kMask);
+            tma_load_2d_mc(st + 2 * a_bytes + w_bytes + crank * w_slice, &map_w_lo, &full_bar[s], kb * BK,
+                           crank * w_rows, kMask);
+          }
           if (++s == p.stages) { s = 0; phase ^= 1; }
         }
       }
@@ -262,7 +302,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                              ((uint32_t)(BM >> 4) << 24);
       uint32_t phase = 0;
       int s = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int g = cid; g < ngroups; g += ncluster, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -281,7 +321,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             umma_bf16(tmem_d, da_hi + adv, dw_lo + adv, idesc, 1u);
             umma_bf16(tmem_d, da_lo + adv, dw_hi + adv, idesc, 1u);
           }
-          umma_commit(&empty_bar[s]);               // frees this smem stage once the MMAs have read it
+          // free this smem stage (in every CTA of the cluster: their producers multicast into it)
+          if (CS == 1) umma_commit(&empty_bar[s]); else umma_commit_mc(&empty_bar[s], kMask);
           if (++s == p.stages) { s = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);           // accumulator complete -> epilogue
@@ -296,7 +337,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const bool vec16_ok = p.c_hi && (p.ldc16 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c_hi) & 7) == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.c_lo) & 7) == 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int g = cid; g < ngroups; g += ncluster, ++it) {
+      const int tile = g * CS + crank;
       const int acc = it & 1;
       mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -364,6 +406,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // nobody exits while a peer may still multicast into / arrive on this CTA
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -408,28 +451,50 @@ int split_launch(const float* A, int64_t lda, int64_t M, int64_t K, __nv_bfloat1
   return GR_OK;
 }
 
+template <int CS>
+int launch_tc_cs(const CUtensorMap& m_a_hi, const CUtensorMap& m_a_lo, const CUtensorMap& m_w_hi,
+                 const CUtensorMap& m_w_lo, const TcPlan& t, const TcParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       220 * 1024));
+    attr_set = true;
+  }
+  const int ngroups = (p.num_tiles + CS - 1) / CS;
+  const int nclusters = std::max(1, std::min(ngroups, sm_count() / CS));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(nclusters * CS));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = t.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<CS>, m_a_hi, m_a_lo, m_w_hi, m_w_lo, p));
+  return GR_OK;
+}
+
 int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int64_t lda16,
               const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int64_t ldw16, const TcPlan& t,
               TcParams p, cudaStream_t stream) {
+  p.n_pad = t.n_pad; p.stages = t.stages;
+  p.num_tiles = (int)ceil_div(p.M, BM);
+  // cluster multicast of W needs 8-row-aligned W slices and at least two tiles
+  int cs = (g_tc_cluster >= 2 && (t.n_pad / 2) % 8 == 0 && p.num_tiles >= 2) ? 2 : 1;
   CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
   if (!make_tmap(&m_a_hi, a_hi, p.M, p.K, lda16, BM) || !make_tmap(&m_a_lo, a_lo, p.M, p.K, lda16, BM) ||
-      !make_tmap(&m_w_hi, w_hi, p.N, p.K, ldw16, t.n_pad) || !make_tmap(&m_w_lo, w_lo, p.N, p.K, ldw16, t.n_pad)) {
+      !make_tmap(&m_w_hi, w_hi, p.N, p.K, ldw16, t.n_pad / cs) ||
+      !make_tmap(&m_w_lo, w_lo, p.N, p.K, ldw16, t.n_pad / cs)) {
     set_error("gr_linear_tc: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned, row strides "
               "multiples of 8 elements)");
     return GR_ERR_CUDA;
   }
-  p.n_pad = t.n_pad; p.stages = t.stages;
-  p.num_tiles = (int)ceil_div(p.M, BM);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       220 * 1024));
-    attr_set = true;
-  }
-  unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, sm_count());
-  linear_tc_kernel<<<grid, kThreads, t.smem_bytes, stream>>>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, p);
-  GR_CHECK_LAUNCH();
-  return GR_OK;
+  if (cs == 2) return launch_tc_cs<2>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, t, p, stream);
+  return launch_tc_cs<1>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, t, p, stream);
 }
 
 }  // namespace

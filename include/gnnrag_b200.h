@@ -48,7 +48,8 @@ typedef enum gr_status {
 int gr_abi_version(void);
 const char* gr_last_error(void);
 /* runtime switches: "agg_tma" (0|1: stage CSR slices with bulk TMA copies), "linear_tc" (0|1: split-bf16
- * tcgen05 GEMM for gr_linear when the shape allows).  Process-wide; set before launching work. */
+ * tcgen05 GEMM for gr_linear when the shape allows), "tc_cluster" (1|2: CTAs per cluster that share the W
+ * tiles of the tcgen05 GEMM through TMA multicast).  Process-wide; set before launching work. */
 int gr_set_option(const char* name, int64_t value);
 static inline int64_t gr_pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
 
