@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=8, help="questions in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agg-tma", type=int, default=None)
+    ap.add_argument("--tc-bk", type=int, default=None)
+    ap.add_argument("--tc-cluster", type=int, default=None)
     return ap.parse_args()
 
 
@@ -211,6 +213,10 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
     if a.agg_tma is not None:
         ops.set_option("agg_tma", a.agg_tma)
+    if a.tc_bk is not None:
+        ops.set_option("tc_bk", a.tc_bk)
+    if a.tc_cluster is not None:
+        ops.set_option("tc_cluster", a.tc_cluster)
     c = S.CONFIGS[a.config]
     B, N, D, I = c["B"], c["N"], c["D"], c["I"]
     args = model_args_for(c, True)

@@ -190,7 +190,7 @@ __device__ __forceinline__ void msg_epilogue(float (&y)[VEC], const float (&xp)[
 // CH = feature chunks per lane (1 or 2): one pass covers 32*VEC*CH columns.
 // PLANES: output goes to the split-bf16 planes (p.out_hi/p.out_lo) instead of fp32 p.out.
 template <int VEC, int CH, int NI, int MODE, bool USE_TMA, bool PLANES>
-__global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
+__global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const AggParams p) {
   __shared__ int32_t s_rowptr[2][kRows + 1];
   __shared__ int2 s_rc[2][kEdgeCap];                       // {table byte offset rel*D*4, float_as_int(c)}
   __shared__ __align__(16) int32_t s_src[USE_TMA ? 2 : 1][USE_TMA ? kEdgeCap + 8 : 1];

@@ -23,13 +23,17 @@ namespace gr {
 
 int g_opt_linear_tc = 0;   // gr_set_option("linear_tc", 0|1): route e2e linears through this kernel
 int g_tc_cluster = 2;      // gr_set_option("tc_cluster", 1|2): CTAs per cluster sharing W tiles by TMA multicast
+int g_tc_bk = 32;          // gr_set_option("tc_bk", 32|64): k-block width (64B / 128B swizzle)
+int g_tc_tma_store = 1;    // gr_set_option("tc_tma_store", 0|1): staged TMA-store epilogue vs direct per-row stores
 
 namespace {
 
 constexpr int BM = 128;          // rows per CTA tile == UMMA_M
-constexpr int BK = 64;           // bf16 elements per k-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
+// k-block width BK (bf16 elements) is a template parameter: 64 (128-byte swizzle rows, 2-3 smem stages)
+// or 32 (64-byte swizzle rows, twice as many, finer stages -> more TMA requests in flight)
+constexpr int kThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue (2 column halves)
+constexpr int kEpiWarps = 8;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -52,16 +56,35 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 row-major [rows, cols] (row stride ld elements) -> tensor map with box {BK cols, box_rows},
 // 128-byte swizzle, zero fill out of bounds.
-bool make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+bool make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+               int bk) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// Output tensor map: row-major [rows, cols] of `elem_bytes`-wide elements, box {16 cols, 128 rows}, no swizzle
+// (the epilogue stages 128x16 chunks densely in smem and TMA-stores them; out-of-range rows/cols are clipped).
+bool make_out_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int elem_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * elem_bytes) % 16 != 0) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {16u, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -146,6 +169,15 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -155,14 +187,16 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-// K-major, 128B-swizzled operand tile: 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1
+// K-major swizzled operand tile whose rows are BK*2 bytes (= the swizzle span): 8-row groups are
+// 8*BK*2 bytes apart (SBO), LBO unused (=1), descriptor version 1, layout SWIZZLE_128B (2) / SWIZZLE_64B (4)
+template <int BK>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows * 128 B
-  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8 * BK * 2) >> 4) << 32;     // stride byte offset: 8 rows
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;      // swizzle mode
   return d;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -202,11 +236,14 @@ struct TcParams {
   __nv_bfloat16* c_hi;      // optional bf16 hi/lo planes of the output (next layer's A operand)
   __nv_bfloat16* c_lo;
   int64_t ldc16;
-  const float* w_score;     // optional: dots[m] = sum_n out[m,n] * w_score[n]   (score_func, reasongnn.py:165)
-  float* dots;
+  const float* w_score;     // optional: score_func dot product (reasongnn.py:165), as two partial sums:
+  float* dots;              //   dots[half*M + m] = sum over this half's columns of out[m,n] * w_score[n]
   int M, N, K, n_pad, stages, num_tiles;
   uint32_t flags;
+  int tma_store;            // 1: epilogue stages 128x16 chunks in smem and writes them with TMA stores
 };
+
+constexpr int kStageOutBytes = BM * 16 * 4 + 2 * BM * 16 * 2;   // per column-half: fp32 8 KB + hi 4 KB + lo 4 KB
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -218,23 +255,32 @@ constexpr int kAccStride = 256;   // TMEM columns per accumulator buffer (two bu
 // the GEMM kernel: persistent over 128-row tiles; TMEM accumulators double-buffered so the epilogue of
 // tile i overlaps the TMA/MMA mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------------
-template <int CS>   // cluster size: the CS CTAs of a cluster each load 1/CS of the W tile and multicast it
+template <int CS, int BK>   // CS: CTAs per cluster sharing W tiles by multicast; BK: k-block width
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                 const TcParams p) {
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c_hi,
+                 const __grid_constant__ CUtensorMap map_c_lo, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages] x {A_hi 16K, A_lo 16K, W_hi n_pad*128, W_lo n_pad*128}, then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int a_bytes = BM * BK * 2;            // 16384
   const int w_bytes = p.n_pad * BK * 2;       // n_pad * 128
   const int stage_bytes = 2 * a_bytes + 2 * w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  // epilogue staging (TMA-store source, must be 128-byte aligned): right after the 1024-aligned stages
+  uint8_t* s_out = smem + (size_t)p.stages * stage_bytes;    // [2 halves] x {fp32 128x16, hi 128x16, lo 128x16}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 2 * kStageOutBytes);
   uint64_t* full_bar = bars;                       // [stages]
   uint64_t* empty_bar = bars + p.stages;           // [stages]
   uint64_t* tmem_full_bar = bars + 2 * p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256] zero padded
+  float* s_ws = s_bias + 256;                                // [256] zero padded
+  for (int i = threadIdx.x; i < 256; i += kThreads) {
+    s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+    s_ws[i] = (p.w_score && i < p.N) ? p.w_score[i] : 0.f;
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + BK - 1) / BK;
@@ -250,7 +296,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);            // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], kEpiWarps);    // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -311,9 +357,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           mbar_wait(&full_bar[s], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t da_hi = make_smem_desc(sa), da_lo = make_smem_desc(sa + a_bytes);
-          const uint64_t dw_hi = make_smem_desc(sa + 2 * a_bytes);
-          const uint64_t dw_lo = make_smem_desc(sa + 2 * a_bytes + w_bytes);
+          const uint64_t da_hi = make_smem_desc<BK>(sa), da_lo = make_smem_desc<BK>(sa + a_bytes);
+          const uint64_t dw_hi = make_smem_desc<BK>(sa + 2 * a_bytes);
+          const uint64_t dw_lo = make_smem_desc<BK>(sa + 2 * a_bytes + w_bytes);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
@@ -330,9 +376,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    // warp e = warp-4: TMEM lane quarter q = warp & 3 (hardware rule), column half = e >> 2
+    const int q = warp & 3, half = (warp - 4) >> 2;
     const int row_in_tile = q * 32 + lane;
     const bool relu = p.flags & GR_LINEAR_RELU;
+    const int nchunks = p.n_pad / 16;
+    const int ch_beg = half == 0 ? 0 : (nchunks + 1) / 2, ch_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
     const bool vec_ok = p.C && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const bool vec16_ok = p.c_hi && (p.ldc16 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c_hi) & 7) == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.c_lo) & 7) == 0);
@@ -345,26 +394,97 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int64_t row = (int64_t)tile * BM + row_in_tile;
       const bool row_ok = row < p.M;
       float* crow = p.C ? p.C + row * p.ldc : nullptr;
+      __nv_bfloat16* hrow = p.c_hi ? p.c_hi + row * p.ldc16 : nullptr;
+      __nv_bfloat16* lrow = p.c_hi ? p.c_lo + row * p.ldc16 : nullptr;
       float dot = 0.f;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
-        if (row_ok) {
+      if (p.tma_store) {
+        // ---- staged epilogue: 128x16 chunk -> smem (dense rows) -> TMA store (clips rows >= M, cols >= N)
+        uint8_t* stg = s_out + (size_t)half * kStageOutBytes;
+        float* s_c = reinterpret_cast<float*>(stg) + row_in_tile * 16;
+        uint32_t* s_h = reinterpret_cast<uint32_t*>(stg + BM * 16 * 4) + row_in_tile * 8;
+        uint32_t* s_l = reinterpret_cast<uint32_t*>(stg + BM * 16 * 4 + BM * 16 * 2) + row_in_tile * 8;
+        const bool issuer = (warp == 4 + 4 * half) && lane == 0;
+        for (int ch = ch_beg; ch < ch_end; ++ch) {
+          const int c0 = ch * 16;
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)c0, r);
+          if (ch == ch_end - 1) {        // last TMEM read of this tile: hand the accumulator back early
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = c0 + j;
-            float x = __uint_as_float(r[j]);
-            if (col < p.N) {
-              if (p.bias) x += __ldg(p.bias + col);
-              if (relu) x = fmaxf(x, 0.f);
-              if (p.w_score) dot = fmaf(x, __ldg(p.w_score + col), dot);
-            }
-            v[j] = x;
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+            const float4 w4 = *reinterpret_cast<const float4*>(s_ws + c0 + j);
+            float x0 = __uint_as_float(r[j]) + b4.x, x1 = __uint_as_float(r[j + 1]) + b4.y;
+            float x2 = __uint_as_float(r[j + 2]) + b4.z, x3 = __uint_as_float(r[j + 3]) + b4.w;
+            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+            dot = fmaf(x0, w4.x, dot); dot = fmaf(x1, w4.y, dot);
+            dot = fmaf(x2, w4.z, dot); dot = fmaf(x3, w4.w, dot);
+            v[j] = x0; v[j + 1] = x1; v[j + 2] = x2; v[j + 3] = x3;
           }
+          uint32_t h[8], l[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+            const float2 hf = __bfloat1622float2(h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[j] - hf.x, v[j + 1] - hf.y);
+            h[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+            l[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          // the previous chunk's TMA stores must have finished READING the staging buffer
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          named_bar_sync(1 + half, 128);
+          if (p.C) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(s_c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (p.c_hi) {
+            *reinterpret_cast<uint4*>(s_h) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(s_h + 4) = make_uint4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<uint4*>(s_l) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(s_l + 4) = make_uint4(l[4], l[5], l[6], l[7]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar_sync(1 + half, 128);
+          if (issuer) {
+            const int m0 = tile * BM;
+            if (p.C) tma_store_2d(&map_c, stg, c0, m0);
+            if (p.c_hi) {
+              tma_store_2d(&map_c_hi, stg + BM * 16 * 4, c0, m0);
+              tma_store_2d(&map_c_lo, stg + BM * 16 * 4 + BM * 16 * 2, c0, m0);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (p.dots && row_ok) p.dots[(int64_t)half * p.M + row] = dot;
+        continue;
+      }
+      for (int ch = ch_beg; ch < ch_end; ++ch) {
+        const int c0 = ch * 16;
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          // columns >= N: accumulator 0 (zero-filled W rows), bias 0, score weight 0 -> contribute 0
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+          const float4 w4 = *reinterpret_cast<const float4*>(s_ws + c0 + j);
+          float x0 = __uint_as_float(r[j]) + b4.x, x1 = __uint_as_float(r[j + 1]) + b4.y;
+          float x2 = __uint_as_float(r[j + 2]) + b4.z, x3 = __uint_as_float(r[j + 3]) + b4.w;
+          if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+          dot = fmaf(x0, w4.x, dot); dot = fmaf(x1, w4.y, dot);
+          dot = fmaf(x2, w4.z, dot); dot = fmaf(x3, w4.w, dot);
+          v[j] = x0; v[j + 1] = x1; v[j + 2] = x2; v[j + 3] = x3;
+        }
+        if (row_ok) {
+          const bool full = c0 + 16 <= p.N;
           if (crow) {
-            if (vec_ok && c0 + 16 <= p.N) {
+            if (vec_ok && full) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -374,35 +494,42 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 if (c0 + j < p.N) crow[c0 + j] = v[j];
             }
           }
-          if (p.c_hi) {
-            __nv_bfloat16 h[16], l[16];
+          if (hrow) {
+            uint32_t h[8], l[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              h[j] = __float2bfloat16_rn(v[j]);
-              l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+            for (int j = 0; j < 16; j += 2) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              const float2 hf = __bfloat1622float2(h2);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[j] - hf.x, v[j + 1] - hf.y);
+              h[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+              l[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
             }
-            __nv_bfloat16* ph = p.c_hi + row * p.ldc16 + c0;
-            __nv_bfloat16* pl = p.c_lo + row * p.ldc16 + c0;
-            if (vec16_ok && c0 + 16 <= p.N) {
+            if (vec16_ok && full) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                *reinterpret_cast<uint2*>(ph + j) = *reinterpret_cast<uint2*>(h + j);
-                *reinterpret_cast<uint2*>(pl + j) = *reinterpret_cast<uint2*>(l + j);
+              for (int j = 0; j < 8; j += 2) {
+                *reinterpret_cast<uint2*>(hrow + c0 + 2 * j) = make_uint2(h[j], h[j + 1]);
+                *reinterpret_cast<uint2*>(lrow + c0 + 2 * j) = make_uint2(l[j], l[j + 1]);
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.N) { ph[j] = h[j]; pl[j] = l[j]; }
+                if (c0 + j < p.N) {
+                  const uint32_t hw = h[j / 2], lw = l[j / 2];
+                  reinterpret_cast<unsigned short*>(hrow)[c0 + j] = (unsigned short)((j & 1) ? (hw >> 16) : (hw & 0xFFFF));
+                  reinterpret_cast<unsigned short*>(lrow)[c0 + j] = (unsigned short)((j & 1) ? (lw >> 16) : (lw & 0xFFFF));
+                }
             }
           }
         }
       }
-      if (p.dots && row_ok) p.dots[row] = dot;
+      if (p.dots && row_ok) p.dots[(int64_t)half * p.M + row] = dot;
       // release the accumulator to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (p.tma_store && lane == 0 && (warp == 4 || warp == 8))
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding TMA stores complete
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -417,21 +544,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
 struct TcPlan {
   int64_t kp;          // plane row stride (elements), multiple of 8
-  int n_pad, stages;
+  int n_pad, stages, bk;
   size_t a_plane_bytes, w_plane_bytes, total_bytes, w_only_bytes, smem_bytes;
   bool ok;
 };
 
 TcPlan plan_tc(int64_t M, int64_t N, int64_t K) {
   TcPlan t{};
+  const int BK = g_tc_bk == 64 ? 64 : 32;
   t.ok = (N >= 8 && N <= 256 && K >= 8 && M >= 1);
   t.kp = (K + 7) / 8 * 8;
   t.n_pad = (int)((N + 15) / 16 * 16);
   const size_t stage = 2 * (size_t)BM * BK * 2 + 2 * (size_t)t.n_pad * BK * 2;
-  int stages = (int)((200 * 1024) / stage);
-  t.stages = stages > 6 ? 6 : stages;
+  // 227 KB usable smem minus alignment slack, bias/score arrays, barriers and the epilogue staging buffers
+  int stages = (int)((227 * 1024 - 1024 - 2048 - 256 - 2 * kStageOutBytes) / stage);
+  t.stages = stages > 8 ? 8 : stages;
   if (t.stages < 2) t.ok = false;
-  t.smem_bytes = (size_t)t.stages * stage + 1024 /*align slack*/ + (2 * t.stages + 4) * 8 + 16;
+  t.bk = BK;
+  t.smem_bytes = (size_t)t.stages * stage + 1024 /*align slack*/ + (2 * t.stages + 4) * 8 + 16 + 2 * 256 * 4 + 2 * kStageOutBytes;
   t.a_plane_bytes = align_up((size_t)M * t.kp * 2, 256);
   t.w_plane_bytes = align_up((size_t)N * t.kp * 2, 256);
   t.total_bytes = 2 * t.a_plane_bytes + 2 * t.w_plane_bytes;
@@ -451,13 +581,14 @@ int split_launch(const float* A, int64_t lda, int64_t M, int64_t K, __nv_bfloat1
   return GR_OK;
 }
 
-template <int CS>
+template <int CS, int BK>
 int launch_tc_cs(const CUtensorMap& m_a_hi, const CUtensorMap& m_a_lo, const CUtensorMap& m_w_hi,
-                 const CUtensorMap& m_w_lo, const TcPlan& t, const TcParams& p, cudaStream_t stream) {
+                 const CUtensorMap& m_w_lo, const CUtensorMap& m_c, const CUtensorMap& m_c_hi,
+                 const CUtensorMap& m_c_lo, const TcPlan& t, const TcParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    GR_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       220 * 1024));
+    GR_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<CS, BK>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int ngroups = (p.num_tiles + CS - 1) / CS;
@@ -474,7 +605,8 @@ int launch_tc_cs(const CUtensorMap& m_a_hi, const CUtensorMap& m_a_lo, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<CS>, m_a_hi, m_a_lo, m_w_hi, m_w_lo, p));
+  GR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<CS, BK>, m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_c, m_c_hi,
+                                   m_c_lo, p));
   return GR_OK;
 }
 
@@ -486,15 +618,27 @@ int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int64_t lda1
   // cluster multicast of W needs 8-row-aligned W slices and at least two tiles
   int cs = (g_tc_cluster >= 2 && (t.n_pad / 2) % 8 == 0 && p.num_tiles >= 2) ? 2 : 1;
   CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
-  if (!make_tmap(&m_a_hi, a_hi, p.M, p.K, lda16, BM) || !make_tmap(&m_a_lo, a_lo, p.M, p.K, lda16, BM) ||
-      !make_tmap(&m_w_hi, w_hi, p.N, p.K, ldw16, t.n_pad / cs) ||
-      !make_tmap(&m_w_lo, w_lo, p.N, p.K, ldw16, t.n_pad / cs)) {
+  if (!make_tmap(&m_a_hi, a_hi, p.M, p.K, lda16, BM, t.bk) || !make_tmap(&m_a_lo, a_lo, p.M, p.K, lda16, BM, t.bk) ||
+      !make_tmap(&m_w_hi, w_hi, p.N, p.K, ldw16, t.n_pad / cs, t.bk) ||
+      !make_tmap(&m_w_lo, w_lo, p.N, p.K, ldw16, t.n_pad / cs, t.bk)) {
     set_error("gr_linear_tc: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned, row strides "
               "multiples of 8 elements)");
     return GR_ERR_CUDA;
   }
-  if (cs == 2) return launch_tc_cs<2>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, t, p, stream);
-  return launch_tc_cs<1>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, t, p, stream);
+  // output tensor maps for the staged TMA-store epilogue (need 16-byte aligned bases and row pitches)
+  CUtensorMap m_c, m_c_hi, m_c_lo;
+  memset(&m_c, 0, sizeof(m_c)); memset(&m_c_hi, 0, sizeof(m_c_hi)); memset(&m_c_lo, 0, sizeof(m_c_lo));
+  bool ok = g_tc_tma_store != 0;
+  if (ok && p.C) ok = make_out_tmap(&m_c, p.C, p.M, p.N, p.ldc, 4);
+  if (ok && p.c_hi) ok = make_out_tmap(&m_c_hi, p.c_hi, p.M, p.N, p.ldc16, 2) &&
+                         make_out_tmap(&m_c_lo, p.c_lo, p.M, p.N, p.ldc16, 2);
+  p.tma_store = ok ? 1 : 0;
+  if (t.bk == 64) {
+    if (cs == 2) return launch_tc_cs<2, 64>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, t, p, stream);
+    return launch_tc_cs<1, 64>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, t, p, stream);
+  }
+  if (cs == 2) return launch_tc_cs<2, 32>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, t, p, stream);
+  return launch_tc_cs<1, 32>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, t, p, stream);
 }
 
 }  // namespace

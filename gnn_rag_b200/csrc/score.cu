@@ -67,13 +67,16 @@ __device__ __forceinline__ float block_reduce(float v, float* sm, bool is_max) {
 }
 
 // logits[n] = (dots[n] + b) + (1-mask[n]) * VERY_NEG   (in place allowed)
-__global__ void logits_from_dots_kernel(const float* __restrict__ dots, const float* __restrict__ bptr,
-                                        const float* __restrict__ mask, float* __restrict__ logits,
-                                        int64_t Nt) {
+__global__ void logits_from_dots_kernel(const float* __restrict__ dots, const float* __restrict__ dots2,
+                                        const float* __restrict__ bptr, const float* __restrict__ mask,
+                                        float* __restrict__ logits, int64_t Nt) {
   const float bias = bptr ? bptr[0] : 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < Nt; n += stride)
-    logits[n] = (dots[n] + bias) + (1.0f - mask[n]) * kVeryNeg;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < Nt; n += stride) {
+    float d = dots[n];
+    if (dots2) d += dots2[n];
+    logits[n] = (d + bias) + (1.0f - mask[n]) * kVeryNeg;
+  }
 }
 
 // one CTA per question: dist[b,:] = softmax(logits[b,:])
@@ -172,15 +175,15 @@ extern "C" int gr_seed_retrieve(const float* seed_info, const float* h, int64_t 
   return GR_OK;
 }
 
-extern "C" int gr_masked_softmax(const float* dots, const float* b_score, const float* mask, float* dist,
-                                 int B, int N, void* stream_) {
+extern "C" int gr_masked_softmax(const float* dots, const float* dots2, const float* b_score,
+                                 const float* mask, float* dist, int B, int N, void* stream_) {
   using namespace gr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   GR_CHECK_ARG(dots && mask && dist, "null pointer");
   GR_CHECK_ARG(B > 0 && N > 0, "bad shape");
   int64_t Nt = (int64_t)B * N;
   int grid = (int)std::min<int64_t>(ceil_div(Nt, 256), 8LL * sm_count());
-  logits_from_dots_kernel<<<grid, 256, 0, stream>>>(dots, b_score, mask, dist, Nt);
+  logits_from_dots_kernel<<<grid, 256, 0, stream>>>(dots, dots2, b_score, mask, dist, Nt);
   GR_CHECK_LAUNCH();
   int threads = N >= 1024 ? 1024 : (N >= 256 ? 256 : 64);
   softmax_kernel<<<B, threads, 0, stream>>>(dist, dist, N);

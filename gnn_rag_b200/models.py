@@ -119,7 +119,8 @@ class BaseModel(nn.Module):
         if planes is not None:
             planes = tuple(p[:, : self.entity_dim] for p in planes)
         if self.encode_type:
-            self.type_layer(db.graph, rel_features, out, planes)
+            # in planes mode nothing reads the fp32 h before the first e2e GEMM rewrites it
+            self.type_layer(db.graph, rel_features, None if planes is not None else out, planes)
         else:
             emb = self.entity_embedding(db.local_entity).view(db.B * db.N, -1).contiguous()
             ops.linear(emb, self.entity_linear.weight, self.entity_linear.bias, out=out)

@@ -154,11 +154,11 @@ class _GraphLayerBase(nn.Module):
         self.cur = 0
         self.Kd = Kd
         if self.use_planes:
-            Kp = (Kd + 7) // 8 * 8
+            Kp = (Kd + 63) // 64 * 64      # 128-byte row pitch: every TMA-stored piece is sector aligned
             self.P = [[torch.empty(Nt, Kp, dtype=torch.bfloat16, device=device) for _ in range(2)]
                       for _ in range(2)]
             self.h32 = torch.empty(Nt, D, dtype=torch.float32, device=device)
-            self.dots = torch.empty(Nt, dtype=torch.float32, device=device)
+            self.dots = torch.empty(2 * Nt, dtype=torch.float32, device=device)
         else:
             self.X = [torch.empty(Nt, Kd, dtype=torch.float32, device=device) for _ in range(2)]
 

@@ -260,7 +260,7 @@ def split_bf16(A, hi, lo):
 def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=None, dots=None, relu=True):
     """tcgen05 split-bf16 GEMM whose A operand already lives in bf16 hi/lo planes [M, >=K].
     Writes any of: fp32 ``out`` [M,N]; ``out_planes`` (hi, lo) [M, >=N] (next layer's h columns);
-    ``dots`` [M] = out @ w_score."""
+    ``dots`` [2*M] = the two column-half partial sums of out @ w_score."""
     M = a_hi.shape[0]
     N = W.shape[0]
     assert a_hi.dtype == torch.bfloat16 and a_hi.stride(1) == 1 and a_hi.stride(0) == a_lo.stride(0)
@@ -280,9 +280,12 @@ def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=
 
 
 def masked_softmax(dots, b_score, mask, B, N):
-    """dist[b,:] = softmax(dots[b,:] + b + (1-mask)*VERY_NEG)  (reasongnn.py:168-169)."""
+    """dist[b,:] = softmax(dots[0,b,:] + dots[1,b,:] + b + (1-mask)*VERY_NEG)  (reasongnn.py:168-169);
+    ``dots`` = the [2, B*N] partial score dots of :func:`linear_tc_planes`."""
     dist = torch.empty(B, N, dtype=torch.float32, device=dots.device)
-    _lib.check(_L().gr_masked_softmax(_p(dots), _p(b_score), _p(mask.contiguous()), _p(dist), B, N, _stream()))
+    d = dots.view(2, -1)
+    _lib.check(_L().gr_masked_softmax(_p(d[0]), _p(d[1]), _p(b_score), _p(mask.contiguous()), _p(dist), B, N,
+                                      _stream()))
     STATS.launches += 2
     return dist
 

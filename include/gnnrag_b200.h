@@ -100,8 +100,9 @@ int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const
 /* Same GEMM with the A operand already in split-bf16 planes (written by gr_aggregate_dual / gr_type_layer /
  * a previous call): no conversion pass over A.  Outputs (each optional, at least one): fp32 C; bf16 planes
  * C_hi/C_lo (row stride ldc16) = the node-embedding columns of the NEXT layer's A operand; and
- * dots[m] = sum_n C[m,n] * w_score[n], the score_func dot product (reasongnn.py:165) fused into the
- * epilogue.  Persistent kernel, TMEM accumulators double-buffered (epilogue overlaps the next tile).
+ * dots (float[2*M]): the score_func dot product (reasongnn.py:165) fused into the epilogue as two partial
+ * sums over the lower / upper half of the output columns, dots[m] + dots[M+m] = sum_n C[m,n] * w_score[n]
+ * (gr_masked_softmax adds them).  Persistent kernel, TMEM accumulators double-buffered (epilogue overlaps the next tile).
  * Workspace: gr_linear_tc_planes_workspace_bytes(N, K) (the W planes), 256-byte aligned. */
 size_t gr_linear_tc_planes_workspace_bytes(int64_t N, int64_t K);
 int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t lda16, const float* W, int64_t ldw,
@@ -166,9 +167,10 @@ int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, const float* w_
 int gr_score_softmax(const float* h, int64_t ldh, const float* w_score, const float* b_score,
                      const float* mask, float* dist, float* logits_out, int B, int N, int D,
                      void* stream);
-/* Same, starting from precomputed dots[b,n] = dot(h[b,n,:], w_score) (gr_linear_tc_planes epilogue). */
-int gr_masked_softmax(const float* dots, const float* b_score, const float* mask, float* dist,
-                      int B, int N, void* stream);
+/* Same, starting from precomputed score dots (gr_linear_tc_planes epilogue): logit = dots[n] (+ dots2[n] if
+ * dots2 != NULL) + b_score + (1-mask)*VERY_NEG. */
+int gr_masked_softmax(const float* dots, const float* dots2, const float* b_score, const float* mask,
+                      float* dist, int B, int N, void* stream);
 
 /* seed_retrieve[b,:] = sum_n seed_info[b,n] * h[b,n,:]  (torch.bmm in QueryReform.forward,
  * gnn/modules/query_update.py:40); only rows with seed_info != 0 are read, in index order. */

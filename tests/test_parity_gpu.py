@@ -133,26 +133,30 @@ def test_linear_tc_split_bf16_vs_fp64(M, N, K):
     assert (got - simt).abs().max().item() < 2e-5 * scale
 
 
+@pytest.mark.parametrize("tma_store", [1, 0])
+@pytest.mark.parametrize("bk", [32, 64])
 @pytest.mark.parametrize("cluster", [1, 2])
-def test_linear_tc_planes_cluster_variants(cluster):
+def test_linear_tc_planes_cluster_variants(cluster, bk, tma_store):
     """Planes-in GEMM (persistent, double-buffered TMEM) with and without W multicast across a CTA pair;
     odd tile counts, fused score dots and plane outputs."""
     torch.manual_seed(2)
     ops.set_option("tc_cluster", cluster)
+    ops.set_option("tc_bk", bk)
+    ops.set_option("tc_tma_store", tma_store)
     try:
         for M, N, K in [(128 * 5 + 37, 200, 1000), (128 * 300, 200, 1000), (77, 64, 96), (128 * 9, 32, 160)]:
             A = torch.randn(M, K, device=DEV)
             W = torch.randn(N, K, device=DEV) / K ** 0.5
             b = torch.randn(N, device=DEV)
             ws = torch.randn(N, device=DEV)
-            Kp = (K + 7) // 8 * 8
+            Kp = (K + 63) // 64 * 64
             hi = torch.empty(M, Kp, dtype=torch.bfloat16, device=DEV)
             lo = torch.empty(M, Kp, dtype=torch.bfloat16, device=DEV)
             ops.split_bf16(A, hi, lo)
             out = torch.empty(M, N, device=DEV)
-            ohi = torch.zeros(M, N + 8, dtype=torch.bfloat16, device=DEV)
-            olo = torch.zeros(M, N + 8, dtype=torch.bfloat16, device=DEV)
-            dots = torch.empty(M, device=DEV)
+            ohi = torch.zeros(M, (N + 8 + 7) // 8 * 8, dtype=torch.bfloat16, device=DEV)
+            olo = torch.zeros_like(ohi)
+            dots = torch.empty(2 * M, device=DEV)
             ops.linear_tc_planes(hi, lo, K, W, b, out=out, out_planes=(ohi, olo), w_score=ws, dots=dots)
             want = torch.relu(A.double() @ W.double().T + b.double())
             scale = (A.double().abs() @ W.double().abs().T).max().item()
@@ -160,9 +164,12 @@ def test_linear_tc_planes_cluster_variants(cluster):
             rec = ohi[:, :N].double() + olo[:, :N].double()
             assert (rec - out.double()).abs().max().item() < 1e-5 * (out.abs().max().item() + 1e-9)
             assert (ohi[:, N:] == 0).all() and (olo[:, N:] == 0).all()
-            assert (dots.double() - out.double() @ ws.double()).abs().max().item() < 1e-4 * (scale + 1)
+            dsum = dots.view(2, M).double().sum(0)
+            assert (dsum - out.double() @ ws.double()).abs().max().item() < 1e-4 * (scale + 1)
     finally:
         ops.set_option("tc_cluster", 2)
+        ops.set_option("tc_bk", 32)
+        ops.set_option("tc_tma_store", 1)
 
 
 def test_forward_with_tc_linear_matches_golden():
