@@ -32,16 +32,17 @@ SIGNATURES = {
     "gr_aggregate": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64,
                              c_i64, c_i64, c_f32p, c_int, c_int, c_int, c_int, c_i64, c_void_p]),
     "gr_aggregate_dual": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p,
-                                  c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_i64,
+                                  c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_i64, c_i64,
                                   c_void_p, c_void_p, c_i64,
                                   c_int, c_int, c_int, c_int, c_i64, c_void_p]),
+    "gr_debug_store_probe": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_void_p]),
     "gr_type_layer": (c_int, [c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_i64,
                               c_void_p, c_void_p, c_i64,
                               c_int, c_int, c_int, c_i64, c_void_p]),
     "gr_linear_tc_planes_workspace_bytes": (c_size, [c_i64, c_i64]),
     "gr_linear_tc_planes": (c_int, [c_void_p, c_void_p, c_i64, c_f32p, c_i64, c_f32p, c_f32p, c_i64,
                                     c_void_p, c_void_p, c_i64, c_f32p, c_f32p, c_i64, c_i64, c_i64,
-                                    c_u32, c_void_p, c_size, c_void_p]),
+                                    c_i64, c_i64, c_u32, c_void_p, c_size, c_void_p]),
     "gr_split_bf16": (c_int, [c_f32p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_void_p]),
     "gr_masked_softmax": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_void_p]),
     "gr_score_softmax": (c_int, [c_f32p, c_i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,

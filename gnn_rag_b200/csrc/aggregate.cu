@@ -189,18 +189,23 @@ __device__ __forceinline__ void msg_epilogue(float (&y)[VEC], const float (&xp)[
 
 // CH = feature chunks per lane (1 or 2): one pass covers 32*VEC*CH columns.
 // PLANES: output goes to the split-bf16 planes (p.out_hi/p.out_lo) instead of fp32 p.out.
-template <int VEC, int CH, int NI, int MODE, bool USE_TMA, bool PLANES>
-__global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const AggParams p) {
+// DT / SEGP: compile-time feature dimension and output-segment pitch (0 = runtime p.D / p.seg_stride_*).  With
+// both fixed every output-segment offset is an immediate, which removes the per-store address arithmetic the
+// generic kernel spends most of its issue slots on; the dual-direction ReaRev layout (segment 2j+d at column
+// (2j+d)*SEGP) is assumed when DT != 0.
+template <int VEC, int CH, int NI, int MODE, bool USE_TMA, bool PLANES, int DT, int SEGP>
+__global__ void __launch_bounds__(kThreads, 2) agg_kernel(const AggParams p) {
   __shared__ int32_t s_rowptr[2][kRows + 1];
   __shared__ int2 s_rc[2][kEdgeCap];                       // {table byte offset rel*D*4, float_as_int(c)}
   __shared__ __align__(16) int32_t s_src[USE_TMA ? 2 : 1][USE_TMA ? kEdgeCap + 8 : 1];
   __shared__ __align__(16) int32_t s_rel[USE_TMA ? 2 : 1][USE_TMA ? kEdgeCap + 8 : 1];
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ unsigned char s_any[2][kRows];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * kRows;
   const int nrows = (int)min((int64_t)kRows, p.Nt - r0);
-  const int D = p.D, N = p.N;
+  const int D = DT ? DT : p.D, N = p.N;
   const int b0 = (int)(r0 / N);                 // one 64-bit division per thread per CTA
   const int rem0 = (int)(r0 - (int64_t)b0 * N);
 
@@ -275,6 +280,20 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
     }
   }
   __syncthreads();
+  // phase 1b: per (direction, row): does any edge carry a non-zero coefficient?  (first layer of every
+  // iteration: the prior is the one-hot seed, almost every row is exactly zero -> pure zero store)
+  if (tid < 2 * kRows) {
+    const int d = tid / kRows, lr = tid % kRows;
+    unsigned char any = 0;
+    if (d < p.ndir && lr < nrows) {
+      const int64_t ebase = s_rowptr[d][0];
+      const int beg = (int)(s_rowptr[d][lr] - ebase), end = (int)(s_rowptr[d][lr + 1] - ebase);
+      if (MODE == MODE_TYPE || end > kEdgeCap) any = 1;
+      for (int i = beg; i < min(end, kEdgeCap) && !any; ++i) any = (s_rc[d][i].y << 1) != 0;   // c != +-0
+    }
+    s_any[d][lr] = any;
+  }
+  __syncthreads();
 
   // ---------------- phase 2: one warp per destination row, lanes across features ----------------------
   constexpr int PASS_COLS = 32 * VEC * CH;
@@ -282,11 +301,16 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
   const int64_t ld = PLANES ? p.ld_planes : p.out_row_stride;
   for (int c0 = 0; c0 < D; c0 += PASS_COLS) {
     const int col0 = c0 + lane * VEC;                 // this lane's column in chunk 0
-    bool act[CH];
+    // columns written per segment: the bf16 planes also get the zero padding up to the 16-column (32-byte)
+    // boundary so that every store completes whole sectors (partial-sector writes halve HBM write throughput)
+    const int seg_pitch_rt = (int)(p.seg_stride_dir > 0 ? p.seg_stride_dir : (p.seg_stride_j > 0 ? p.seg_stride_j : D));
+    const int Dw = PLANES ? (DT ? SEGP : min((D + 15) / 16 * 16, MODE == MODE_TYPE ? (int)ld : max(seg_pitch_rt, D))) : D;
+    bool act[CH], wr[CH];
     const char* tcol[2][CH];     // per-direction table column bases; inactive lanes are clamped to column 0
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
       act[ch] = col0 + ch * CHW < D;
+      wr[ch] = col0 + ch * CHW < Dw;
       const int lc = act[ch] ? col0 + ch * CHW : 0;
 #pragma unroll
       for (int d = 0; d < 2; ++d)
@@ -298,7 +322,9 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
     for (int d = 0; d < 2; ++d)
 #pragma unroll
       for (int j = 0; j < NI; ++j)
-        seg[d][j] = (int)(d * p.seg_stride_dir + (int64_t)(p.j0 + j) * p.seg_stride_j);
+        seg[d][j] = DT ? (d * SEGP + j * 2 * SEGP)   // + j0 * 2 * SEGP folded into the lane base pointers
+                       : (int)(d * p.seg_stride_dir + (int64_t)(p.j0 + j) * p.seg_stride_j);
+    const int64_t j0off = DT ? (int64_t)p.j0 * 2 * SEGP : 0;
 
     int cur_b = -1;
     float xp[NI][CH][VEC], xn[NI][CH][VEC];   // relu(ins), relu(-ins) of the current question
@@ -310,14 +336,20 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
         for (int k = 0; k < VEC; ++k) xp[j][ch][k] = xn[j][ch][k] = 0.f;
 
     // per-lane base pointers of the tile (row 0, this lane's chunk-0 column)
-    float* const out_lane = PLANES ? nullptr : p.out + r0 * ld + p.out_col0 + col0;
-    __nv_bfloat16* const hi_lane = PLANES ? p.out_hi + r0 * ld + p.out_col0 + col0 : nullptr;
-    __nv_bfloat16* const lo_lane = PLANES ? p.out_lo + r0 * ld + p.out_col0 + col0 : nullptr;
+    float* const out_lane = PLANES ? nullptr : p.out + r0 * ld + p.out_col0 + col0 + j0off;
+    __nv_bfloat16* const hi_lane = PLANES ? p.out_hi + r0 * ld + p.out_col0 + col0 + j0off : nullptr;
+    __nv_bfloat16* const lo_lane = PLANES ? p.out_lo + r0 * ld + p.out_col0 + col0 + j0off : nullptr;
 
+    const int lr_switch = N - rem0;      // first tile row that belongs to question b0 + 1 (N >= kRows assumed
+                                         // for the fast path; the while loop below handles tiny N)
     for (int lr = warp; lr < nrows; lr += kWarps) {
       if (MODE == MODE_MSG) {
-        int q = rem0 + lr, b = b0;
-        while (q >= N) { q -= N; ++b; }
+        int b = b0 + (lr >= lr_switch ? 1 : 0);
+        if (N < kRows) {                 // rare: several questions inside one tile
+          int q = rem0 + lr;
+          b = b0;
+          while (q >= N) { q -= N; ++b; }
+        }
         if (b != cur_b) {
           cur_b = b;
 #pragma unroll
@@ -327,9 +359,9 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
               float x[VEC];
               ldg_vec<VEC>(x, p.ins + ((int64_t)b * p.I + p.j0 + j) * D + (act[ch] ? col0 + ch * CHW : 0));
 #pragma unroll
-              for (int k = 0; k < VEC; ++k) {
-                xp[j][ch][k] = fmaxf(x[k], 0.f);
-                xn[j][ch][k] = fmaxf(-x[k], 0.f);
+              for (int k = 0; k < VEC; ++k) {   // lanes past D carry x = 0 -> they produce exact zeros
+                xp[j][ch][k] = act[ch] ? fmaxf(x[k], 0.f) : 0.f;
+                xn[j][ch][k] = act[ch] ? fmaxf(-x[k], 0.f) : 0.f;
               }
             }
         }
@@ -346,6 +378,19 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
           if (pred) st_vec<VEC>(orow + off, y);
         }
       };
+      auto store_zero = [&](int off, bool pred) {
+        if constexpr (PLANES) {
+          SplitVec<VEC> sv;
+#pragma unroll
+          for (int k = 0; k < (VEC + 1) / 2; ++k) sv.h[k] = sv.l[k] = 0u;
+          if (pred) st_split<VEC>(hrow + off, lrow + off, sv);
+        } else {
+          float z[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) z[k] = 0.f;
+          if (pred) st_vec<VEC>(orow + off, z);
+        }
+      };
       float tsum[CH][VEC];   // MODE_TYPE: sum over both directions
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
@@ -356,33 +401,22 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
       for (int d = 0; d < 2; ++d) {
         if (d >= p.ndir) break;
         const AggDir& dd = p.dir[d];
-        const int64_t ebase = s_rowptr[d][0];
-        const int beg = (int)(s_rowptr[d][lr] - ebase), end = (int)(s_rowptr[d][lr + 1] - ebase);
-        const int fast_end = min(end, kEdgeCap);
+        const int ebase = s_rowptr[d][0];
+        const int beg = s_rowptr[d][lr] - ebase, end = s_rowptr[d][lr + 1] - ebase;
 
-        // does any edge of this row carry a non-zero coefficient?  (first layer of every iteration: the
-        // prior is the one-hot seed, almost every row is exactly zero -> pure zero store)
-        bool any = (MODE == MODE_TYPE) || (end > kEdgeCap);
-        if (MODE == MODE_MSG && !any) {
-          for (int i = beg + lane; i < fast_end; i += 32) any |= (s_rc[d][i].y << 1) != 0;   // c != +-0
-          any = __any_sync(0xffffffffu, any);
-        }
         if (MODE == MODE_MSG && p.possible && c0 == 0 && d == 0 && p.j0 == 0) {   // nsm_gnn.py:101-103
           float cs = 0.f;
-          for (int i = beg; i < fast_end; ++i) cs += __int_as_float(s_rc[d][i].y);
+          for (int i = beg; i < min(end, kEdgeCap); ++i) cs += __int_as_float(s_rc[d][i].y);
           for (int i = max(beg, kEdgeCap); i < end; ++i)
-            cs += edge_coeff<MODE>(p, dd, ebase + i, dd.src[ebase + i]);
+            cs += edge_coeff<MODE>(p, dd, (int64_t)ebase + i, dd.src[(int64_t)ebase + i]);
           if (lane == 0) p.possible[r0 + lr] = cs > 1e-10f ? 1.f : 0.f;
         }
 
-        if (MODE == MODE_MSG && !any) {
-          float z[VEC];
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) z[k] = 0.f;
+        if (MODE == MODE_MSG && !s_any[d][lr]) {
 #pragma unroll
           for (int j = 0; j < NI; ++j)
 #pragma unroll
-            for (int ch = 0; ch < CH; ++ch) store(seg[d][j] + ch * CHW, act[ch], z);
+            for (int ch = 0; ch < CH; ++ch) store_zero(seg[d][j] + ch * CHW, wr[ch]);
           continue;
         }
 
@@ -392,12 +426,17 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
 #pragma unroll
           for (int k = 0; k < VEC; ++k) A[ch][k] = S[ch][k] = 0.f;
 
-        int i = beg;
-        for (; i + 4 <= fast_end; i += 4) {
+        // edges in branch-free blocks of 4: slots past the row end re-read the last edge with c forced to
+        // 0 (fma(0, x, acc) == acc exactly for finite table values), so every block issues its loads together
+        const int fast_end = min(end, kEdgeCap);
+        for (int i = beg; i < fast_end; i += 4) {
           int2 m[4];
           float v[4][CH][VEC];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) m[u] = s_rc[d][i + u];
+          for (int u = 0; u < 4; ++u) {
+            m[u] = s_rc[d][min(i + u, fast_end - 1)];
+            if (i + u >= fast_end) m[u].y = 0;
+          }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -408,17 +447,8 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
             for (int ch = 0; ch < CH; ++ch)
               accumulate<VEC, MODE>(A[ch], S[ch], v[u][ch], __int_as_float(m[u].y));
         }
-        for (; i < fast_end; ++i) {
-          const int2 m = s_rc[d][i];
-#pragma unroll
-          for (int ch = 0; ch < CH; ++ch) {
-            float v[VEC];
-            ldg_vec<VEC>(v, tcol[d][ch] + (uint32_t)m.x);
-            accumulate<VEC, MODE>(A[ch], S[ch], v, __int_as_float(m.y));
-          }
-        }
-        for (; i < end; ++i) {   // slow path: the tile's edge slice overflowed the staging buffer (hubs)
-          const int64_t e = ebase + i;
+        for (int i = max(beg, kEdgeCap); i < end; ++i) {   // slow path: edge slice overflowed the staging buffer
+          const int64_t e = (int64_t)ebase + i;
           const int s = dd.src ? dd.src[e] : 0;
           const uint32_t off = (uint32_t)dd.rel[e] * (uint32_t)D * 4u;
           const float c = edge_coeff<MODE>(p, dd, e, s);
@@ -449,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
             for (int j = 0; j < NI; ++j) {
               float y[VEC];
               msg_epilogue<VEC>(y, xp[j][ch], xn[j][ch], A[ch], T);
-              store(seg[d][j] + ch * CHW, act[ch], y);
+              store(seg[d][j] + ch * CHW, wr[ch], y);
             }
           }
         } else {
@@ -464,32 +494,47 @@ __global__ void __launch_bounds__(kThreads, (NI <= 2 ? 3 : 2)) agg_kernel(const 
         for (int ch = 0; ch < CH; ++ch) {
           float y[VEC];
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) y[k] = fmaxf(tsum[ch][k], 0.f);
-          store(ch * CHW, act[ch], y);
+          for (int k = 0; k < VEC; ++k) y[k] = act[ch] ? fmaxf(tsum[ch][k], 0.f) : 0.f;
+          store(ch * CHW, wr[ch], y);
         }
       }
     }
   }
 }
 
-template <int VEC, int CH, int NI, int MODE>
-int launch_agg2(const AggParams& p, bool tma, cudaStream_t stream) {
+template <int VEC, int CH, int NI, int MODE, int DT, int SEGP>
+int launch_agg3(const AggParams& p, bool tma, cudaStream_t stream) {
   unsigned grid = (unsigned)ceil_div(p.Nt, kRows);
   if (p.out) {
-    if (tma)
-      agg_kernel<VEC, CH, NI, MODE, true, false><<<grid, kThreads, 0, stream>>>(p);
+    if (tma && DT == 0)
+      agg_kernel<VEC, CH, NI, MODE, (DT == 0), false, DT, SEGP><<<grid, kThreads, 0, stream>>>(p);
     else
-      agg_kernel<VEC, CH, NI, MODE, false, false><<<grid, kThreads, 0, stream>>>(p);
+      agg_kernel<VEC, CH, NI, MODE, false, false, DT, SEGP><<<grid, kThreads, 0, stream>>>(p);
     GR_CHECK_LAUNCH();
   }
   if (p.out_hi) {   // split-bf16 planes (a second launch only if the caller asked for both formats)
-    if (tma)
-      agg_kernel<VEC, CH, NI, MODE, true, true><<<grid, kThreads, 0, stream>>>(p);
+    if (tma && DT == 0)
+      agg_kernel<VEC, CH, NI, MODE, (DT == 0), true, DT, SEGP><<<grid, kThreads, 0, stream>>>(p);
     else
-      agg_kernel<VEC, CH, NI, MODE, false, true><<<grid, kThreads, 0, stream>>>(p);
+      agg_kernel<VEC, CH, NI, MODE, false, true, DT, SEGP><<<grid, kThreads, 0, stream>>>(p);
     GR_CHECK_LAUNCH();
   }
   return GR_OK;
+}
+
+template <int VEC, int CH, int NI, int MODE>
+int launch_agg2(const AggParams& p, bool tma, cudaStream_t stream) {
+  // specialised instance for the WebQSP-shape feature width (BASELINE cfg1/2/4: D = 200) in the
+  // dual-direction ReaRev layout; everything else takes the runtime-D kernel
+  if constexpr (VEC == 4 && CH == 2 && MODE == MODE_MSG) {
+    if (p.D == 200 && p.ndir == 2 && !tma) {
+      if (p.seg_stride_dir == 200 && p.seg_stride_j == 400)
+        return launch_agg3<VEC, CH, NI, MODE, 200, 200>(p, tma, stream);
+      if (p.seg_stride_dir == 208 && p.seg_stride_j == 416)   // 32-byte aligned bf16 plane segments
+        return launch_agg3<VEC, CH, NI, MODE, 200, 208>(p, tma, stream);
+    }
+  }
+  return launch_agg3<VEC, CH, NI, MODE, 0, 0>(p, tma, stream);
 }
 
 template <int MODE>
@@ -541,6 +586,51 @@ int launch_agg(AggParams p, cudaStream_t stream) {
 }  // namespace
 }  // namespace gr
 
+namespace gr {
+namespace {
+// Store-pattern probe (scripts/agg_probe.py): writes zeros to the neighbour columns of the bf16 planes with
+// the aggregation kernel's exact thread->address mapping (64-row CTA tiles, one warp per row, lanes across
+// 2 chunks of 4 bf16, 8 stores per direction) but WITHOUT phase 1 / edge work.  mode 0: STG.64 per lane as the
+// kernel does; mode 1: same bytes written as contiguous 16-byte lanes (row-major sweep of the 1600-byte span).
+__global__ void __launch_bounds__(kThreads, 2)
+agg_store_probe_kernel(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t Nt, int64_t ld, int col_start, int ncols,
+                       int mode) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * kRows;
+  const int nrows = (int)min((int64_t)kRows, Nt - r0);
+  for (int lr = warp; lr < nrows; lr += kWarps) {
+    __nv_bfloat16* h = hi + (r0 + lr) * ld + col_start;
+    __nv_bfloat16* l = lo + (r0 + lr) * ld + col_start;
+    if (mode == 0) {          // 8-byte lanes (what the planes kernel does)
+      for (int c = lane * 4; c < ncols; c += 128) {
+        *reinterpret_cast<uint2*>(h + c) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(l + c) = make_uint2(0u, 0u);
+      }
+    } else if (mode == 1) {   // 16-byte lanes
+      for (int c = lane * 8; c < ncols; c += 256) {
+        *reinterpret_cast<uint4*>(h + c) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(l + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else {                  // single plane, 16-byte lanes, twice the columns (= one fp32-wide row)
+      for (int c = lane * 8; c < 2 * ncols; c += 256)
+        *reinterpret_cast<uint4*>(h + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+}  // namespace
+}  // namespace gr
+
+extern "C" int gr_debug_store_probe(void* hi, void* lo, int64_t Nt, int64_t ld, int col_start, int ncols,
+                                    int mode, void* stream_) {
+  using namespace gr;
+  GR_CHECK_ARG(hi && lo && Nt > 0, "bad args");
+  unsigned grid = (unsigned)ceil_div(Nt, kRows);
+  agg_store_probe_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), Nt, ld, col_start, ncols, mode);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
 extern "C" int gr_aggregate(const int32_t* rowptr, const int32_t* src, const int32_t* rel,
                             const float* w, const float* prior, const float* table, const float* ins,
                             float* out, int64_t out_row_stride, int64_t out_col0, int64_t seg_stride,
@@ -564,9 +654,9 @@ extern "C" int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, 
                                  const float* w_t, const int32_t* rowptr_h, const int32_t* src_h,
                                  const int32_t* rel_h, const float* w_h, const float* prior,
                                  const float* table_fwd, const float* table_inv, const float* ins,
-                                 float* out, int64_t out_row_stride, int64_t out_col0, void* out_hi,
-                                 void* out_lo, int64_t ld_planes, int B, int N, int D, int I, int64_t F,
-                                 void* stream_) {
+                                 float* out, int64_t out_row_stride, int64_t out_col0, int64_t seg_pitch,
+                                 void* out_hi, void* out_lo, int64_t ld_planes, int B, int N, int D, int I,
+                                 int64_t F, void* stream_) {
   using namespace gr;
   GR_CHECK_ARG(rowptr_t && rowptr_h && prior && table_fwd && table_inv && ins, "null pointer");
   GR_CHECK_ARG(out || (out_hi && out_lo), "no output requested");
@@ -581,7 +671,9 @@ extern "C" int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, 
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   p.ld_planes = out_hi ? ld_planes : 0;
   p.out_row_stride = out_row_stride; p.out_col0 = out_col0;
-  p.seg_stride_j = 2 * (int64_t)D; p.seg_stride_dir = D;
+  if (seg_pitch <= 0) seg_pitch = D;
+  GR_CHECK_ARG(seg_pitch >= D, "seg_pitch smaller than D");
+  p.seg_stride_j = 2 * seg_pitch; p.seg_stride_dir = seg_pitch;
   p.B = B; p.N = N; p.D = D; p.I = I; p.j0 = 0;
   p.Nt = (int64_t)B * N; p.Fpad = gr_pad4(F);
   return launch_agg<MODE_MSG>(p, reinterpret_cast<cudaStream_t>(stream_));

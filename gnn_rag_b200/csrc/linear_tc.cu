@@ -91,6 +91,23 @@ bool make_out_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols,
 // ---------------------------------------------------------------------------------------------------
 // fp32 -> (hi, lo) bf16 planes
 // ---------------------------------------------------------------------------------------------------
+// W [N, nseg*seg] dense -> hi/lo planes [N, >= nseg*pitch] with segment s at columns [s*pitch, s*pitch+seg),
+// zeros in the padding columns (matches the padded activation-plane layout)
+__global__ void split_bf16_seg_kernel(const float* __restrict__ W, int64_t ldw, int64_t N, int64_t Kpad,
+                                      int seg, int pitch, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, int64_t ldo) {
+  const int64_t total = N * Kpad;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t n = i / Kpad, k = i - n * Kpad;
+    const int sidx = (int)(k / pitch), c = (int)(k - (int64_t)sidx * pitch);
+    float v = c < seg ? __ldg(W + n * ldw + (int64_t)sidx * seg + c) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[n * ldo + k] = h;
+    lo[n * ldo + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 __global__ void split_bf16_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int64_t K,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                   int64_t ldo, int vec_ok, int vec_st) {
@@ -630,8 +647,10 @@ int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int64_t lda1
   memset(&m_c, 0, sizeof(m_c)); memset(&m_c_hi, 0, sizeof(m_c_hi)); memset(&m_c_lo, 0, sizeof(m_c_lo));
   bool ok = g_tc_tma_store != 0;
   if (ok && p.C) ok = make_out_tmap(&m_c, p.C, p.M, p.N, p.ldc, 4);
-  if (ok && p.c_hi) ok = make_out_tmap(&m_c_hi, p.c_hi, p.M, p.N, p.ldc16, 2) &&
-                         make_out_tmap(&m_c_lo, p.c_lo, p.M, p.N, p.ldc16, 2);
+  // the planes also receive the (exactly zero) columns N .. round16(N): whole 32-byte sectors per row
+  const int64_t n16 = std::min<int64_t>((p.N + 15) / 16 * 16, p.ldc16);
+  if (ok && p.c_hi) ok = make_out_tmap(&m_c_hi, p.c_hi, p.M, n16, p.ldc16, 2) &&
+                         make_out_tmap(&m_c_lo, p.c_lo, p.M, n16, p.ldc16, 2);
   p.tma_store = ok ? 1 : 0;
   if (t.bk == 64) {
     if (cs == 2) return launch_tc_cs<2, 64>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, t, p, stream);
@@ -709,14 +728,17 @@ extern "C" int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t
 extern "C" int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t lda16, const float* W,
                                    int64_t ldw, const float* bias, float* C, int64_t ldc, void* C_hi,
                                    void* C_lo, int64_t ldc16, const float* w_score, float* dots, int64_t M,
-                                   int64_t N, int64_t K, uint32_t flags, void* workspace,
-                                   size_t workspace_bytes, void* stream_) {
+                                   int64_t N, int64_t K, int64_t k_seg, int64_t k_seg_pitch, uint32_t flags,
+                                   void* workspace, size_t workspace_bytes, void* stream_) {
   using namespace gr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   GR_CHECK_ARG(A_hi && A_lo && W && workspace, "null pointer");
   GR_CHECK_ARG(C || C_hi, "no output requested");
   GR_CHECK_ARG(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
-  GR_CHECK_ARG(lda16 >= K && lda16 % 8 == 0 && ldw >= K, "lda16 must be >= K and a multiple of 8");
+  const bool segmented = k_seg > 0 && k_seg_pitch > k_seg;
+  GR_CHECK_ARG(lda16 >= K && lda16 % 8 == 0, "lda16 must be >= K and a multiple of 8");
+  GR_CHECK_ARG(!segmented || K % k_seg_pitch == 0, "K must be a multiple of k_seg_pitch");
+  GR_CHECK_ARG(ldw >= (segmented ? K / k_seg_pitch * k_seg : K), "ldw smaller than the weight row length");
   GR_CHECK_ARG(!C || ldc >= N, "ldc smaller than N");
   GR_CHECK_ARG(!C_hi || (C_lo && ldc16 >= N), "C_lo missing or ldc16 smaller than N");
   GR_CHECK_ARG(!dots || w_score, "dots requested without w_score");
@@ -734,7 +756,15 @@ extern "C" int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t l
   char* ws = reinterpret_cast<char*>(workspace);
   __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + t.w_plane_bytes);
-  int rc = split_launch(W, ldw, N, K, w_hi, w_lo, t.kp, stream);
+  int rc = GR_OK;
+  if (segmented) {
+    int64_t work = N * K;
+    int grid = (int)std::min<int64_t>(ceil_div(work, 256), 32LL * sm_count());
+    split_bf16_seg_kernel<<<grid, 256, 0, stream>>>(W, ldw, N, K, (int)k_seg, (int)k_seg_pitch, w_hi, w_lo, t.kp);
+    GR_CHECK_LAUNCH();
+  } else {
+    rc = split_launch(W, ldw, N, K, w_hi, w_lo, t.kp, stream);
+  }
   if (rc != GR_OK) return rc;
   TcParams p{};
   p.bias = bias; p.C = C; p.ldc = ldc;

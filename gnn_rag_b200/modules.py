@@ -148,15 +148,27 @@ class _GraphLayerBase(nn.Module):
           the A-operand layout of the tcgen05 e2e GEMM; h additionally lives in fp32 ``h32`` [B*N, D].
       fp32: ping-pong fp32 buffers X[2] feeding the exact-fp32 SIMT linear (ops.TC_LINEAR = False)."""
 
+    _plane_cache = {}     # (device, Nt, Kp) -> zero-initialised ping-pong planes, reused across forwards
+
     def _alloc(self, Nt, Kd, device):
         D = self.entity_dim
         self.use_planes = bool(ops.TC_LINEAR) and 8 <= D <= 256
         self.cur = 0
         self.Kd = Kd
         if self.use_planes:
-            Kp = (Kd + 63) // 64 * 64      # 128-byte row pitch: every TMA-stored piece is sector aligned
-            self.P = [[torch.empty(Nt, Kp, dtype=torch.bfloat16, device=device) for _ in range(2)]
-                      for _ in range(2)]
+            # every segment ([h | nb_0 | nb_1 ...], D columns each) starts on a 32-byte sector: pitch = D rounded
+            # up to 16 bf16 columns (a 16-byte-misaligned segment start halves HBM write throughput on B200);
+            # padding columns stay zero forever (nothing writes them), so the padded GEMM is exact
+            self.Dp = (D + 15) // 16 * 16
+            self.Kpad = Kd // D * self.Dp
+            Kp = (self.Kpad + 63) // 64 * 64    # 128-byte row pitch: every TMA-stored piece is sector aligned
+            key = (str(device), Nt, Kp, D)
+            if key not in _GraphLayerBase._plane_cache:
+                _GraphLayerBase._plane_cache.clear()
+                _GraphLayerBase._plane_cache[key] = [
+                    [torch.zeros(Nt, Kp, dtype=torch.bfloat16, device=device) for _ in range(2)]
+                    for _ in range(2)]
+            self.P = _GraphLayerBase._plane_cache[key]
             self.h32 = torch.empty(Nt, D, dtype=torch.float32, device=device)
             self.dots = torch.empty(2 * Nt, dtype=torch.float32, device=device)
         else:
@@ -176,8 +188,8 @@ class _GraphLayerBase(nn.Module):
         if self.use_planes:
             hi, lo = self.P[self.cur]
             nhi, nlo = self.P[1 - self.cur]
-            ops.linear_tc_planes(hi, lo, self.Kd, e2e.weight, e2e.bias, out=self.h32, out_planes=(nhi, nlo),
-                                 w_score=sw, dots=self.dots, relu=True)
+            ops.linear_tc_planes(hi, lo, self.Kpad, e2e.weight, e2e.bias, out=self.h32, out_planes=(nhi, nlo),
+                                 w_score=sw, dots=self.dots, relu=True, k_seg=D, k_seg_pitch=self.Dp)
             self.cur = 1 - self.cur
             return ops.masked_softmax(self.dots, sb, mask, self.B, self.N)
         X, Xn = self.X[self.cur], self.X[1 - self.cur]
@@ -232,9 +244,11 @@ class ReasonGNNLayer(_GraphLayerBase):
         g = self.graph
         tf, ti = self.tables[step]
         wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
-        ops.aggregate_dual(g, current_dist, tf, ti, relational_ins,
-                           None if self.use_planes else self.X[self.cur], D, wt, wh,
-                           planes=self.cur_planes())
+        if self.use_planes:
+            ops.aggregate_dual(g, current_dist, tf, ti, relational_ins, None, self.Dp, wt, wh,
+                               planes=self.cur_planes(), seg_pitch=self.Dp)
+        else:
+            ops.aggregate_dual(g, current_dist, tf, ti, relational_ins, self.X[self.cur], D, wt, wh)
         dist = self._e2e_and_score(getattr(self, "e2e_linear" + str(step)), self.local_entity_mask)
         return dist, self.h_view
 
@@ -277,7 +291,7 @@ class NSMLayer(_GraphLayerBase):
             ops.aggregate(g, "fwd", current_dist, self.tables[step], relational_ins.view(self.B, 1, D),
                           out=self.nb32, out_col0=0, seg_stride=D, w=w, possible=self.possible)
             hi, lo = self.P[self.cur]
-            ops.split_bf16(self.nb32, hi[:, D:], lo[:, D:])
+            ops.split_bf16(self.nb32, hi[:, self.Dp:], lo[:, self.Dp:])
         else:
             ops.aggregate(g, "fwd", current_dist, self.tables[step], relational_ins.view(self.B, 1, D),
                           out=self.X[self.cur], out_col0=D, seg_stride=D, w=w, possible=self.possible)

@@ -210,7 +210,8 @@ def aggregate(g, direction, prior, table, ins, out=None, out_col0=0, seg_stride=
     return out
 
 
-def aggregate_dual(g, prior, table_fwd, table_inv, ins, out, out_col0, w_t=None, w_h=None, planes=None):
+def aggregate_dual(g, prior, table_fwd, table_inv, ins, out, out_col0, w_t=None, w_h=None, planes=None,
+                   seg_pitch=0):
     """Both directions of one ReaRev layer: out[:, out_col0 + (2j+dir)*D : +D] (reasongnn.py:150-161).
     ``planes`` = (hi, lo) bf16 [B*N, ld] tensors: write the split-bf16 A-operand planes (``out`` may be
     None)."""
@@ -224,7 +225,7 @@ def aggregate_dual(g, prior, table_fwd, table_inv, ins, out, out_col0, w_t=None,
         rc = _L().gr_aggregate_dual(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t),
                                     _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(w_h),
                                     _p(prior), _p(table_fwd), _p(table_inv), _p(ins), _p(out),
-                                    out.stride(0) if out is not None else 0, out_col0,
+                                    out.stride(0) if out is not None else 0, out_col0, seg_pitch,
                                     _p(hi), _p(lo), hi.stride(0) if hi is not None else 0,
                                     B, g.N, D, I, g.F, _stream())
     _lib.check(rc)
@@ -257,14 +258,19 @@ def split_bf16(A, hi, lo):
     STATS.launches += 1
 
 
-def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=None, dots=None, relu=True):
+def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=None, dots=None, relu=True,
+                     k_seg=0, k_seg_pitch=0):
     """tcgen05 split-bf16 GEMM whose A operand already lives in bf16 hi/lo planes [M, >=K].
     Writes any of: fp32 ``out`` [M,N]; ``out_planes`` (hi, lo) [M, >=N] (next layer's h columns);
     ``dots`` [2*M] = the two column-half partial sums of out @ w_score."""
     M = a_hi.shape[0]
     N = W.shape[0]
     assert a_hi.dtype == torch.bfloat16 and a_hi.stride(1) == 1 and a_hi.stride(0) == a_lo.stride(0)
-    assert W.shape[1] == K and W.stride(1) == 1
+    if k_seg and k_seg_pitch > k_seg:
+        assert K % k_seg_pitch == 0 and W.shape[1] == K // k_seg_pitch * k_seg
+    else:
+        assert W.shape[1] == K
+    assert W.stride(1) == 1
     L = _L()
     nbytes = L.gr_linear_tc_planes_workspace_bytes(N, K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=a_hi.device)
@@ -272,8 +278,8 @@ def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=
     rc = L.gr_linear_tc_planes(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(W), W.stride(0), _p(bias),
                                _p(out), out.stride(0) if out is not None else 0,
                                _p(chi), _p(clo), chi.stride(0) if chi is not None else 0,
-                               _p(w_score), _p(dots), M, N, K, LINEAR_RELU if relu else 0,
-                               _p(ws), nbytes, _stream())
+                               _p(w_score), _p(dots), M, N, K, k_seg, k_seg_pitch,
+                               LINEAR_RELU if relu else 0, _p(ws), nbytes, _stream())
     _lib.check(rc)
     STATS.launches += 2
     return out

@@ -103,11 +103,15 @@ int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const
  * dots (float[2*M]): the score_func dot product (reasongnn.py:165) fused into the epilogue as two partial
  * sums over the lower / upper half of the output columns, dots[m] + dots[M+m] = sum_n C[m,n] * w_score[n]
  * (gr_masked_softmax adds them).  Persistent kernel, TMEM accumulators double-buffered (epilogue overlaps the next tile).
+ * Segmented K: when k_seg_pitch > k_seg > 0 the A planes hold K/k_seg_pitch segments of k_seg valid columns
+ * at pitch k_seg_pitch (zero padding in between) while W is the dense [N, (K/k_seg_pitch)*k_seg] torch weight;
+ * the W planes are built in the padded layout.  K is the padded length.
  * Workspace: gr_linear_tc_planes_workspace_bytes(N, K) (the W planes), 256-byte aligned. */
 size_t gr_linear_tc_planes_workspace_bytes(int64_t N, int64_t K);
 int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t lda16, const float* W, int64_t ldw,
                         const float* bias, float* C, int64_t ldc, void* C_hi, void* C_lo, int64_t ldc16,
                         const float* w_score, float* dots, int64_t M, int64_t N, int64_t K,
+                        int64_t k_seg, int64_t k_seg_pitch,
                         uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
 /* fp32 [M,K] (row stride lda) -> bf16 hi/lo planes (row stride ld_out, multiple of 8). */
 int gr_split_bf16(const float* A, int64_t lda, int64_t M, int64_t K, void* hi, void* lo, int64_t ld_out,
@@ -128,7 +132,10 @@ int gr_split_bf16(const float* A, int64_t lda, int64_t M, int64_t K, void* hi, v
  * gr_aggregate_dual: both directions of one ReaRev GNN layer in one launch; instruction j writes
  *     forward  (tail CSR, table_fwd) -> columns out_col0 + (2j  )*D
  *     inverse  (head CSR, table_inv) -> columns out_col0 + (2j+1)*D
- * which is the concat order of ReasonGNNLayer.forward (reasongnn.py:150-161).
+ * which is the concat order of ReasonGNNLayer.forward (reasongnn.py:150-161).  seg_pitch (0 = D) is the
+ * column distance between consecutive segments: the bf16 planes use a pitch rounded up to 16 columns so that
+ * every segment starts on a 32-byte sector (measured on B200: a 16-byte-misaligned segment start halves the
+ * achievable write bandwidth, scripts/agg_probe.py).
  *
  * Split-bf16 planes (optional, gr_aggregate_dual / gr_type_layer): when out_hi/out_lo are non-NULL the
  * result is ALSO (or, with out == NULL, only) written as two bf16 matrices with row stride ld_planes and
@@ -148,9 +155,13 @@ int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, const int32
                       const float* w_t, const int32_t* rowptr_h, const int32_t* src_h,
                       const int32_t* rel_h, const float* w_h, const float* prior,
                       const float* table_fwd, const float* table_inv, const float* ins,
-                      float* out, int64_t out_row_stride, int64_t out_col0,
+                      float* out, int64_t out_row_stride, int64_t out_col0, int64_t seg_pitch,
                       void* out_hi, void* out_lo, int64_t ld_planes,
                       int B, int N, int D, int I, int64_t F, void* stream);
+
+/* Diagnostic only (scripts/agg_probe.py): replays the aggregation kernel's store pattern without any edge work. */
+int gr_debug_store_probe(void* hi, void* lo, int64_t Nt, int64_t ld, int col_start, int ncols, int mode,
+                         void* stream);
 
 int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, const float* w_t,
                   const int32_t* rowptr_h, const int32_t* rel_h, const float* w_h,
