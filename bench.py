@@ -311,10 +311,18 @@ def run_ours(a):
     dense = [ms for i, (ms, _) in enumerate(agg) if (i % per_step) % K != 0] if per_step else []
     seedl = [ms for i, (ms, _) in enumerate(agg) if (i % per_step) % K == 0] if per_step else []
     abytes = agg_algorithmic_bytes(B, N, F, D, I, R1)
+    traffic = None     # dram__bytes_read+write of the dense-prior launch from the committed ncu --set full capture
+    try:
+        import glob
+        tj = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+        if tj and a.config == "cfg2":
+            traffic = json.load(open(tj[-1])).get("agg_dense_traffic_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
     dense_ms = float(np.mean(dense)) if dense else float("nan")
     achieved = abytes / (dense_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "agg_kernel (gr_aggregate_dual)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dense_ms,
                 "launches_per_step": per_step,
                 "seed_prior_launch_ms": float(np.mean(seedl)) if seedl else None,
