@@ -272,7 +272,13 @@ def run_ours(a):
     launches = ops.STATS.launches
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
     agg = [(s.elapsed_time(e), tag) for s, e, tag in ops.STATS.agg_events]
+    # clocks are sampled over the device-timed region only: nvidia-smi polling takes a driver lock and
+    # perturbs the wall-clock e2e loop below (measured: 5.5 ms/step alone vs 8-19 ms with the sampler on)
+    clocks = sampler.stop() if rank == 0 else None
     # ---- e2e: host (pinned) batch in, retrieved candidate lists out -------------------------------
+    for _ in range(2):      # warm the host-batch path (allocator, pinned staging)
+        _l, _p, pd_, _ = model(pinned)
+        evaluate.retrieve(pd_, model.last_batch, S.WEBQSP_NUM_ENTITY, eps)
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
@@ -284,7 +290,6 @@ def run_ours(a):
         h2d, d2h = model.last_batch.h2d_bytes, nb
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     # ---- max over ranks ------------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
