@@ -1,0 +1,134 @@
+"""GPU: the other BASELINE configurations (size-independent properties + kernel-level parity at full size) and the
+`.info` wire format the LLM stage consumes."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gnn_rag_b200 as G
+from gnn_rag_b200 import batching, evaluate, ops, synthetic as S
+from oracle import kgqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _model(c, model="ReaRev", **kw):
+    args = S.model_args(model, entity_dim=c["D"], num_iter=c["T"], num_ins=c["I"], num_gnn=c["K"], num_step=c["K"],
+                        use_cuda=True, **kw)
+    torch.manual_seed(0)
+    cls = G.NSM if model == "NSM" else G.ReaRev
+    return cls(dict(args), S.WEBQSP_NUM_ENTITY, S.WEBQSP_NUM_RELATION, S.WEBQSP_NUM_WORD).eval(), args
+
+
+def test_cfg5_stress_graph_aggregate_parity_and_forward_properties():
+    """cfg5: 100k-node / 1M-edge subgraph, 400-dim features (generic runtime-D kernel, two column passes, hub rows
+    beyond the smem edge staging, fp32 SIMT linear because D > 256)."""
+    c = S.CONFIGS["cfg5"]
+    b = S.make_batch(3, B=1, N=c["N"], E=c["E"], powerlaw=True, with_weights=False)
+    db = batching.stage_batch(b, torch.device(DEV), S.WEBQSP_NUM_RELATION + 1)
+    db.graph.check_status()
+    rs = np.random.RandomState(0)
+    D = c["D"]
+    table = torch.from_numpy(rs.randn(S.WEBQSP_NUM_RELATION + 1, D).astype(np.float32))
+    ins = torch.from_numpy(rs.randn(1, 1, D).astype(np.float32))
+    prior = torch.softmax(torch.from_numpy(rs.randn(1, c["N"]).astype(np.float32)), 1)
+    got = ops.aggregate(db.graph, "fwd", prior.to(DEV), table.to(DEV), ins.to(DEV)).cpu()
+    mats = O.FactMats(b[2], 1, c["N"], False)
+    want = O.reason_layer(mats, prior, ins[:, 0, :], table, torch.eye(D), None, False)
+    assert (got - want).abs().max().item() <= 5e-5 * (want.abs().max().item() + 1e-12)
+    m, args = _model(c)
+    _, _, d1, _ = m(b)
+    _, _, d2, _ = m(b)
+    assert torch.equal(d1, d2)                                        # deterministic at stress size
+    assert abs(float(d1.sum()) - 1.0) < 1e-4 and (d1 >= 0).all()
+    ret, _ = evaluate.retrieve(d1, m.last_batch, S.WEBQSP_NUM_ENTITY, args["eps"])
+    assert len(ret) == 1 and len(ret[0]) > 0
+
+
+def test_cfg3_cwq_shape_forward_properties():
+    """cfg3 shape (10k nodes, 40k edges, 4 hops, 3 instructions) at B=8: split-bf16 planes with 7 segments,
+    the NI=3 aggregation instance, GEMM K = 7*208."""
+    c = dict(S.CONFIGS["cfg3"], B=8)
+    m, args = _model(c)
+    b = S.make_batch(5, B=c["B"], N=c["N"], E=c["E"], n_real=9000, with_weights=False, multi_seed=True)
+    _, _, d1, _ = m(b)
+    _, _, d2, _ = m(b)
+    assert torch.equal(d1, d2)
+    assert torch.allclose(d1.sum(1), torch.ones(c["B"], device=DEV), atol=1e-4)
+    assert (d1[:, 9000:] == 0).all()
+    # and against the CPU oracle on the first two questions (block-diagonal independence)
+    from gnn_rag_b200 import parallel
+    small = parallel.shard_batch(b, 0, 4)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    _, _, want = O.forward(sd, args, S.WEBQSP_NUM_ENTITY, S.WEBQSP_NUM_WORD, small)
+    _, _, got, _ = m(small)
+    err = ((got.cpu() - want).abs() / want.clamp_min(1e-30)).max().item()
+    assert err < 1e-3, err
+
+
+def test_nsm_webqsp_shape_vs_oracle_and_reason_kb():
+    c = dict(S.CONFIGS["cfg2"], B=4)
+    m, args = _model(c, "NSM", reason_kb=True)
+    b = S.make_batch(9, B=4, N=c["N"], E=c["E"], with_weights=False)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    _, _, want = O.forward(sd, args, S.WEBQSP_NUM_ENTITY, S.WEBQSP_NUM_WORD, b)
+    _, _, got, _ = m(b)
+    nz = want > 0
+    assert ((got.cpu() > 0) == nz).all()                              # possible_tail mask identical
+    assert ((got.cpu() - want).abs()[nz] / want[nz]).max().item() < 1e-3
+
+
+class _FakeLoader:
+    """Just enough of SingleDataLoader (gnn/dataset_load.py:599-629) for Evaluator.evaluate."""
+
+    def __init__(self, B, N, E, num_batches):
+        self.num_data, self.bs = B * num_batches, B
+        self.max_local_entity = N
+        self.batches = [S.make_batch(20 + i, B=B, N=N, E=E, num_entity=500, num_relation=30, num_word=60,
+                                     test=True, with_weights=False) for i in range(num_batches)]
+
+    def reset_batches(self, is_sequential=True):
+        pass
+
+    def get_quest(self):
+        return ["question %d " % i for i in range(self.num_data)]
+
+    def get_batch(self, iteration, batch_size, fact_dropout, test=False):
+        return self.batches[iteration]
+
+
+def test_info_jsonl_matches_shipped_schema(tmp_path):
+    """Rows written by Evaluator.evaluate(write_info=True) parse exactly like the reference's shipped
+    llm/results/gnn/*/test.info (first 3 rows kept in tests/golden/test_info_sample.jsonl)."""
+    sample = [json.loads(l) for l in open(os.path.join(HERE, "golden", "test_info_sample.jsonl"))]
+    args = S.model_args("ReaRev", entity_dim=32, num_iter=3, num_ins=2, num_gnn=2, word_dim=16, use_cuda=True,
+                        checkpoint_dir=str(tmp_path) + "/", experiment_name="t")
+    torch.manual_seed(0)
+    m = G.ReaRev(dict(args), 500, 30, 60).eval()
+    with torch.no_grad():
+        m.reasoning.score_func.weight.mul_(30.0)
+    entity2id = {"m.%04d" % i: i for i in range(500)}
+    ev = G.Evaluator(args, m, entity2id, {}, torch.device(DEV))
+    loader = _FakeLoader(B=4, N=64, E=200, num_batches=2)
+    f1, h1, em = ev.evaluate(loader, test_batch_size=4, write_info=True)
+    rows = [json.loads(l) for l in open(os.path.join(str(tmp_path), "t_test.info"))]
+    assert len(rows) == 8 and 0.0 <= f1 <= 1.0
+    for r in rows:
+        assert list(r.keys()) == list(sample[0].keys())               # same keys, same order
+        for k, v in sample[0].items():
+            assert type(r[k]) is type(v), k
+        assert all(isinstance(c[0], str) and isinstance(c[1], float) for c in r["cand"])
+        probs = [c[1] for c in r["cand"]]
+        assert probs == sorted(probs, reverse=True)
+    # metrics agree with the reference's formula (oracle f1_and_hits) on the same retrieved lists
+    b = loader.batches[0]
+    _, _, dist, _ = m(b[:-1])
+    ret, _ = evaluate.retrieve(dist, m.last_batch, 500, args["eps"])
+    for q in range(4):
+        ids = ret[q].ent.tolist()
+        p, r_, f, h, e, _ = evaluate.f1_and_hits(list(b[-1][q]), ids)
+        assert (p, r_, f, h) == O.f1_and_hits(list(b[-1][q]), ids, ids[0] if ids else -1)
