@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--agg-tma", type=int, default=None)
     ap.add_argument("--tc-bk", type=int, default=None)
     ap.add_argument("--tc-cluster", type=int, default=None)
+    ap.add_argument("--cuda-graph", type=int, default=1,
+                    help="1: run the step through gnn_rag_b200.GraphedStep (CUDA-graph replay over static buffers)")
     return ap.parse_args()
 
 
@@ -233,13 +235,23 @@ def run_ours(a):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     eps = args["eps"]
 
-    def step(batch):
+    gs = G.GraphedStep(model, S.WEBQSP_NUM_ENTITY) if a.cuda_graph else None
+
+    def step_eager(batch):
         _loss, _pred, pred_dist, _ = model(batch)
         cand = ops.rank_candidates(pred_dist, model.last_batch.local_entity,
                                    model.last_batch.query_entities, S.WEBQSP_NUM_ENTITY, eps)
         if world > 1:
             parallel.all_gather_scores(pred_dist, B * world)
         return pred_dist, cand
+
+    def step(batch):
+        if gs is None:
+            return step_eager(batch)
+        out = gs(batch)                     # copies the inputs into the static buffers, replays the graph
+        if world > 1:
+            parallel.all_gather_scores(out.pred_dist, B * world)
+        return out.pred_dist, out
 
     def barrier():
         if world > 1:
@@ -253,9 +265,22 @@ def run_ours(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- timed region: K steps, device-resident inputs, CUDA events, L2 flushed between steps -------
+    # ---- eager replica of the timed region: per-launch CUDA events around every aggregation launch (the
+    # live roofline measurement) and the launch count; with --cuda-graph the same kernels are replayed from the
+    # graph in the timed region below, where per-launch events cannot be recorded
     ops.STATS.reset()
     ops.STATS.time_agg = True
+    for _ in range(a.steps):
+        flush.fill_(1)
+        step_eager(dev_batch)
+    barrier()
+    ops.STATS.time_agg = False
+    launches = ops.STATS.launches
+    agg = [(s.elapsed_time(e), tag) for s, e, tag in ops.STATS.agg_events]
+    for _ in range(3):
+        step(dev_batch)
+    barrier()
+    # ---- timed region: K steps, device-resident inputs, CUDA events, L2 flushed between steps -------
     evs = []
     barrier()
     wall0 = time.perf_counter()
@@ -268,25 +293,30 @@ def run_ours(a):
         evs.append((s, e))
     barrier()
     wall = time.perf_counter() - wall0
-    ops.STATS.time_agg = False
-    launches = ops.STATS.launches
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
-    agg = [(s.elapsed_time(e), tag) for s, e, tag in ops.STATS.agg_events]
     # clocks are sampled over the device-timed region only: nvidia-smi polling takes a driver lock and
     # perturbs the wall-clock e2e loop below (measured: 5.5 ms/step alone vs 8-19 ms with the sampler on)
     clocks = sampler.stop() if rank == 0 else None
     # ---- e2e: host (pinned) batch in, retrieved candidate lists out -------------------------------
+    def e2e_step():
+        if gs is None:
+            _loss, _pred, pred_dist, _ = model(pinned)
+            retrieved, nb = evaluate.retrieve(pred_dist, model.last_batch, S.WEBQSP_NUM_ENTITY, eps)
+        else:
+            out = gs(pinned)
+            pred_dist = out.pred_dist
+            retrieved, nb = gs.retrieve(out)
+        if world > 1:
+            parallel.all_gather_scores(pred_dist, B * world)
+        return nb
+
     for _ in range(2):      # warm the host-batch path (allocator, pinned staging)
-        _l, _p, pd_, _ = model(pinned)
-        evaluate.retrieve(pd_, model.last_batch, S.WEBQSP_NUM_ENTITY, eps)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(a.steps):
-        _loss, _pred, pred_dist, _ = model(pinned)
-        retrieved, nb = evaluate.retrieve(pred_dist, model.last_batch, S.WEBQSP_NUM_ENTITY, eps)
-        if world > 1:
-            parallel.all_gather_scores(pred_dist, B * world)
+        nb = e2e_step()
         h2d, d2h = model.last_batch.h2d_bytes, nb
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -330,6 +360,7 @@ def run_ours(a):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dense_ms,
                 "launches_per_step": per_step,
+                "measured_in": "eager replica of the timed region (same process, same inputs, L2 flushed)",
                 "seed_prior_launch_ms": float(np.mean(seedl)) if seedl else None,
                 "agg_share_of_step": (sum(ms for ms, _ in agg) / dev_ms) if dev_ms else None}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
@@ -338,6 +369,7 @@ def run_ours(a):
             "config": config_dict(a.config, c, {
                 "global_questions": world * B, "l2": "256 MiB flush write between timed steps",
                 "timing": "CUDA events per step on the launch stream, max over ranks",
+                "cuda_graph": bool(a.cuda_graph),
                 "wall_s_timed_region_incl_flush": wall}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps},

@@ -5,5 +5,6 @@ Public surface mirrors the reference (cmavro/GNN-RAG ``gnn/``):
 """
 from .models import NSM, ReaRev  # noqa: F401
 from .evaluate import Evaluator, retrieve  # noqa: F401
+from .graphed import GraphedStep  # noqa: F401
 
-__all__ = ["ReaRev", "NSM", "Evaluator", "retrieve"]
+__all__ = ["ReaRev", "NSM", "Evaluator", "retrieve", "GraphedStep"]

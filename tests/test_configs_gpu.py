@@ -132,3 +132,20 @@ def test_info_jsonl_matches_shipped_schema(tmp_path):
         ids = ret[q].ent.tolist()
         p, r_, f, h, e, _ = evaluate.f1_and_hits(list(b[-1][q]), ids)
         assert (p, r_, f, h) == O.f1_and_hits(list(b[-1][q]), ids, ids[0] if ids else -1)
+
+
+def test_graphed_step_matches_eager():
+    """CUDA-graph replay of (CSR batching + forward + ranking) == eager path, bit for bit, across batches."""
+    c = dict(S.CONFIGS["cfg2"], B=8, N=500, E=1500)
+    m, args = _model(c)
+    gs = G.GraphedStep(m, S.WEBQSP_NUM_ENTITY)
+    for seed in (11, 12, 13):
+        b = S.make_batch(seed, B=c["B"], N=c["N"], E=c["E"], with_weights=False)
+        out = gs(b)
+        ret_g, _ = gs.retrieve(out)
+        dist_g = out.pred_dist.clone()
+        loss, pred, dist, _ = m(b)
+        ret_e, _ = evaluate.retrieve(dist, m.last_batch, S.WEBQSP_NUM_ENTITY, args["eps"])
+        assert torch.equal(dist_g, dist)
+        assert float(out.loss) == float(loss)
+        assert [r.ent.tolist() for r in ret_g] == [r.ent.tolist() for r in ret_e]
