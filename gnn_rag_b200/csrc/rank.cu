@@ -8,6 +8,8 @@
 // (key = (~bits(p)) << 32 | local_index: ascending key == descending p, ascending index on ties), and the
 // same sequential float64 running sum.  Integer/bit work end to end: bit-exact w.r.t. the reference
 // given the same probabilities.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace gr {
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(kRankThreads)
 rank_kernel(const float* __restrict__ dist, const int64_t* __restrict__ local_entity,
             const float* __restrict__ query_entities, int64_t pad_id, double eps, double ignore_prob,
             int32_t* __restrict__ cand_idx, int32_t* __restrict__ cand_count,
-            int32_t* __restrict__ cand_total, int N, unsigned long long* __restrict__ ws) {
+            int32_t* __restrict__ cand_total, int N, unsigned long long* __restrict__ ws, int exact_ok) {
   __shared__ unsigned long long s_keys[kSmemKeys];
   __shared__ int s_woff[kRankThreads / 32 + 1];
   __shared__ int s_base;
@@ -54,7 +56,8 @@ rank_kernel(const float* __restrict__ dist, const int64_t* __restrict__ local_en
   const int64_t* le = local_entity + (int64_t)b * N;
   const float* qe = query_entities + (int64_t)b * N;
   unsigned long long* gkeys = ws + (int64_t)b * N;
-  if (tid == 0) s_base = 0;
+  __shared__ int s_bad;      // a kept term > 1.0: not a probability -> no exactness argument, sequential sum
+  if (tid == 0) { s_base = 0; s_bad = 0; }
   __syncthreads();
   // 1. order-preserving compaction of surviving candidates into gkeys
   for (int base = 0; base < N; base += kRankThreads) {
@@ -67,6 +70,7 @@ rank_kernel(const float* __restrict__ dist, const int64_t* __restrict__ local_en
       bool is_pad = le[n] == pad_id;                      // :201
       bool small = (double)pv < ignore_prob;              // :203 (python float compare)
       keep = !is_seed && !is_pad && !small;
+      if (keep && !(pv <= 1.0f)) s_bad = 1;
     }
     unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) s_woff[wid + 1] = __popc(bal);
@@ -96,8 +100,42 @@ rank_kernel(const float* __restrict__ dist, const int64_t* __restrict__ local_en
     __threadfence_block();
   }
   bitonic_sort_u64(keys, total);
-  // 3. eps-mass prefix with the sequential float64 sum of f1_and_hits (evaluate.py:41-50)
-  if (tid == 0) {
+  // 3. eps-mass prefix = first i with (sum_{k<=i} p_k in float64) > eps (f1_and_hits, evaluate.py:41-50).
+  //    The reference adds sequentially in python floats (fp64).  Every surviving p_k is an fp32 value
+  //    >= ignore_prob, so with exact_ok (host: 24 + ceil(log2(1/ignore_prob)) + 1 <= 53) every partial sum of
+  //    any subset is exactly representable in fp64: the fp64 sum is ORDER-INDEPENDENT and a parallel scan is
+  //    bit-identical to the sequential loop.  Otherwise fall back to the sequential loop.
+  if (exact_ok && !s_bad) {
+    __shared__ double s_wsum[kRankThreads / 32];
+    __shared__ double s_carry;
+    __shared__ int s_first;
+    if (tid == 0) { s_carry = 0.0; s_first = total; }
+    __syncthreads();
+    for (int base = 0; base < total && s_first == total; base += kRankThreads) {
+      const int i = base + tid;
+      double v = 0.0;
+      if (i < total) v = (double)__uint_as_float(0xFFFFFFFFu - (unsigned)(keys[i] >> 32));
+      double x = v;                                   // inclusive warp scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_wsum[wid] = x;
+      __syncthreads();
+      double off = s_carry;
+      for (int w = 0; w < wid; ++w) off += s_wsum[w];
+      const double cum = off + x;
+      if (i < total && cum > eps) atomicMin(&s_first, i);
+      __syncthreads();
+      if (tid == kRankThreads - 1) s_carry = cum;     // carry = inclusive sum of the whole chunk
+      __syncthreads();
+    }
+    if (tid == 0) {
+      cand_count[b] = s_first < total ? s_first + 1 : total;
+      cand_total[b] = total;
+    }
+  } else if (tid == 0) {
     double tp = 0.0;
     int cnt = 0;
     for (int i = 0; i < total; ++i) {
@@ -137,9 +175,19 @@ extern "C" int gr_rank_candidates(const float* dist, const int64_t* local_entity
     return GR_ERR_WORKSPACE;
   }
   double ignore_prob = (1 - eps) / N;   // evaluate.py:156
+  // order-independence of the fp64 running sum (see rank_kernel step 3)
+  int exact_ok = 0;
+  if (ignore_prob > 0.0 && ignore_prob < 1.0) {
+    int e_min;
+    frexp(ignore_prob, &e_min);                       // ignore_prob = m * 2^e_min, m in [0.5, 1)
+    // all terms are multiples of 2^(e_min - 24); terms are <= 1 (checked on device) and the scan only trusts
+    // partial sums up to the first crossing of eps (< eps + 1 < 2): 24 + (1 - e_min) + 1 bits suffice
+    int bits = 24 + (1 - e_min) + 1;
+    exact_ok = bits <= 53 && eps < 1.0;
+  }
   rank_kernel<<<B, kRankThreads, 0, stream>>>(dist, local_entity, query_entities, pad_id, eps,
                                               ignore_prob, cand_idx, cand_count, cand_total, N,
-                                              reinterpret_cast<unsigned long long*>(workspace));
+                                              reinterpret_cast<unsigned long long*>(workspace), exact_ok);
   GR_CHECK_LAUNCH();
   return GR_OK;
 }

@@ -178,8 +178,8 @@ class ReaRev(BaseModel):
     def get_rel_feature(self):                                   # rearev.py:91-111
         if self.rel_texts is None:
             lin = self.relation_linear
-            rel = ops.linear(self.relation_embedding.weight, lin.weight, lin.bias)
-            rel_inv = ops.linear(self.relation_embedding_inv.weight, lin.weight, lin.bias)
+            rel = ops.rel_linear(self.relation_embedding.weight, lin.weight, lin.bias)
+            rel_inv = ops.rel_linear(self.relation_embedding_inv.weight, lin.weight, lin.bias)
             return rel, rel_inv
         ins = self.instruction
         rel = ins.question_emb(self.rel_features)
@@ -247,7 +247,7 @@ class NSM(BaseModel):
 
     def get_rel_feature(self):                                   # nsm.py:97-111
         lin = self.relation_linear1
-        return ops.linear(self.relation_embedding.weight, lin.weight, lin.bias)
+        return ops.rel_linear(self.relation_embedding.weight, lin.weight, lin.bias)
 
     @torch.no_grad()
     def forward(self, batch, training=False):

@@ -33,7 +33,7 @@ class TypeLayer(nn.Module):
         self.norm_rel = norm_rel
 
     def forward(self, graph, rel_features, out, planes=None):
-        table = ops.linear(rel_features, self.kb_self_linear.weight, self.kb_self_linear.bias)
+        table = ops.rel_linear(rel_features, self.kb_self_linear.weight, self.kb_self_linear.bias)
         wt, wh = (graph.wr_t, graph.wr_h) if self.norm_rel else (None, None)
         ops.type_layer(graph, table, out, wt, wh, planes=planes)
         return out
@@ -233,8 +233,8 @@ class ReasonGNNLayer(_GraphLayerBase):
             pe = getattr(self, "pos_emb" + str(k)).weight if self.use_posemb else None
             pei = getattr(self, "pos_emb_inv" + str(k)).weight if self.use_posemb else None
             nrel = pe.shape[0] if pe is not None else 0
-            tf = ops.linear(rel_features, lin.weight, lin.bias, addend=pe, addend_rows=nrel)
-            ti = ops.linear(rel_features_inv, lin.weight, lin.bias, addend=pei, addend_rows=nrel)
+            tf = ops.rel_linear(rel_features, lin.weight, lin.bias, addend=pe, addend_rows=nrel)
+            ti = ops.rel_linear(rel_features_inv, lin.weight, lin.bias, addend=pei, addend_rows=nrel)
             self.tables.append((tf, ti))
 
     def forward(self, current_dist, relational_ins, step=0):
@@ -276,7 +276,7 @@ class NSMLayer(_GraphLayerBase):
         self.tables = []
         for k in range(self.num_steps):
             lin = getattr(self, "rel_linear" + str(k))
-            self.tables.append(ops.linear(rel_features, lin.weight, lin.bias))
+            self.tables.append(ops.rel_linear(rel_features, lin.weight, lin.bias))
         self.possible = torch.empty(db.B * db.N, dtype=torch.float32, device=db.local_entity.device)
         if self.use_planes:
             self.nb32 = torch.empty(db.B * db.N, D, dtype=torch.float32, device=db.local_entity.device)
