@@ -115,17 +115,23 @@ class BaseModel(nn.Module):
 
     def _get_ent_init(self, db, rel_features, layer):              # rearev.py:79-88 / nsm.py:84-94
         """Initial node embeddings, written straight into the reasoning layer's h slot(s)."""
-        out, planes = layer.h_view, layer.cur_planes()
+        planes = layer.cur_planes()
         if planes is not None:
             planes = tuple(p[:, : self.entity_dim] for p in planes)
+            out = layer.h32
+        else:
+            out = layer.h_view
         if self.encode_type:
             # in planes mode nothing reads the fp32 h before the first e2e GEMM rewrites it
             self.type_layer(db.graph, rel_features, None if planes is not None else out, planes)
+            if planes is not None:
+                layer.h32_valid = False
         else:
             emb = self.entity_embedding(db.local_entity).view(db.B * db.N, -1).contiguous()
             ops.linear(emb, self.entity_linear.weight, self.entity_linear.bias, out=out)
             if planes is not None:
                 ops.split_bf16(out, planes[0], planes[1])
+                layer.h32_valid = True
         return out
 
     # base_model.py:186-215 + rearev.py:156-160
@@ -206,8 +212,9 @@ class ReaRev(BaseModel):
         for _t in range(self.num_iter):                          # rearev.py:206-221
             relation_ins = torch.stack(instructions, dim=1)
             dist = db.seed_dist                                  # distribution resets to the seed (:208)
-            for j in range(self.num_gnn):
-                dist, h = self.reasoning(dist, relation_ins, step=j)
+            for j in range(self.num_gnn):                        # only the last layer's h feeds the reform
+                dist, hj = self.reasoning(dist, relation_ins, step=j, need_h=(j == self.num_gnn - 1))
+                h = hj if hj is not None else h
             self.dist_history.append(dist)
             instructions = [getattr(self, "reform" + str(j))(instructions[j], h, db.query_entities, B, N)
                             for j in range(I)]

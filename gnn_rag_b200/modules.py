@@ -170,26 +170,39 @@ class _GraphLayerBase(nn.Module):
                     for _ in range(2)]
             self.P = _GraphLayerBase._plane_cache[key]
             self.h32 = torch.empty(Nt, D, dtype=torch.float32, device=device)
+            self.h32_valid = False
             self.dots = torch.empty(2 * Nt, dtype=torch.float32, device=device)
         else:
             self.X = [torch.empty(Nt, Kd, dtype=torch.float32, device=device) for _ in range(2)]
 
     @property
     def h_view(self):
-        return self.h32 if self.use_planes else self.X[self.cur][:, : self.entity_dim]
+        """fp32 node embeddings [B*N, D].  In planes mode the fp32 copy is only written when a consumer asked for
+        it (``need_h32``); otherwise it is rebuilt on demand from the hi/lo planes (exact to 2^-18)."""
+        if not self.use_planes:
+            return self.X[self.cur][:, : self.entity_dim]
+        if not self.h32_valid:
+            D = self.entity_dim
+            hi, lo = self.P[self.cur]
+            torch.add(hi[:, :D].float(), lo[:, :D].float(), out=self.h32)
+            self.h32_valid = True
+        return self.h32
 
     def cur_planes(self):
         return tuple(self.P[self.cur]) if self.use_planes else None
 
-    def _e2e_and_score(self, e2e, mask):
-        """h <- relu(e2e([h, nb...])); dist = softmax(score_func(h) + mask)."""
+    def _e2e_and_score(self, e2e, mask, need_h32=True):
+        """h <- relu(e2e([h, nb...])); dist = softmax(score_func(h) + mask).  ``need_h32``: also write the fp32
+        copy of h (only the instruction update after the last layer of an iteration reads it)."""
         D = self.entity_dim
         sw, sb = self.score_func.weight.view(-1), self.score_func.bias
         if self.use_planes:
             hi, lo = self.P[self.cur]
             nhi, nlo = self.P[1 - self.cur]
-            ops.linear_tc_planes(hi, lo, self.Kpad, e2e.weight, e2e.bias, out=self.h32, out_planes=(nhi, nlo),
-                                 w_score=sw, dots=self.dots, relu=True, k_seg=D, k_seg_pitch=self.Dp)
+            ops.linear_tc_planes(hi, lo, self.Kpad, e2e.weight, e2e.bias, out=self.h32 if need_h32 else None,
+                                 out_planes=(nhi, nlo), w_score=sw, dots=self.dots, relu=True, k_seg=D,
+                                 k_seg_pitch=self.Dp)
+            self.h32_valid = bool(need_h32)
             self.cur = 1 - self.cur
             return ops.masked_softmax(self.dots, sb, mask, self.B, self.N)
         X, Xn = self.X[self.cur], self.X[1 - self.cur]
@@ -237,9 +250,10 @@ class ReasonGNNLayer(_GraphLayerBase):
             ti = ops.rel_linear(rel_features_inv, lin.weight, lin.bias, addend=pei, addend_rows=nrel)
             self.tables.append((tf, ti))
 
-    def forward(self, current_dist, relational_ins, step=0):
+    def forward(self, current_dist, relational_ins, step=0, need_h=True):
         """One GNN layer (reasongnn.py:134-174): aggregate both directions for every instruction into the
-        concat slots, h <- relu(e2e_k([h, nb...])), score, masked softmax."""
+        concat slots, h <- relu(e2e_k([h, nb...])), score, masked softmax.  Returns (dist, h) with h = None when
+        ``need_h`` is False (the caller does not read the embeddings of this layer)."""
         D = self.entity_dim
         g = self.graph
         tf, ti = self.tables[step]
@@ -249,8 +263,8 @@ class ReasonGNNLayer(_GraphLayerBase):
                                planes=self.cur_planes(), seg_pitch=self.Dp)
         else:
             ops.aggregate_dual(g, current_dist, tf, ti, relational_ins, self.X[self.cur], D, wt, wh)
-        dist = self._e2e_and_score(getattr(self, "e2e_linear" + str(step)), self.local_entity_mask)
-        return dist, self.h_view
+        dist = self._e2e_and_score(getattr(self, "e2e_linear" + str(step)), self.local_entity_mask, need_h)
+        return dist, (self.h_view if need_h else None)
 
 
 class NSMLayer(_GraphLayerBase):
@@ -296,4 +310,4 @@ class NSMLayer(_GraphLayerBase):
             ops.aggregate(g, "fwd", current_dist, self.tables[step], relational_ins.view(self.B, 1, D),
                           out=self.X[self.cur], out_col0=D, seg_stride=D, w=w, possible=self.possible)
         mask = self.local_entity_mask * self.possible if self.reason_kb else self.local_entity_mask
-        return self._e2e_and_score(getattr(self, "e2e_linear" + str(step)), mask)
+        return self._e2e_and_score(getattr(self, "e2e_linear" + str(step)), mask, need_h32=False)
