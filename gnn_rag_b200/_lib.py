@@ -45,6 +45,11 @@ SIGNATURES = {
                                     c_i64, c_i64, c_u32, c_void_p, c_size, c_void_p]),
     "gr_split_bf16": (c_int, [c_f32p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_void_p]),
     "gr_masked_softmax": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_void_p]),
+    "gr_frontier_rows": (c_int, [c_i32p, c_i32p, c_i32p, c_i32p, c_f32p, c_i64, c_i32p, c_i32p, c_void_p]),
+    "gr_frontier_fixup": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p, c_f32p,
+                                  c_f32p, c_f32p, c_f32p, c_void_p, c_void_p, c_i64, c_f32p, c_i64, c_f32p,
+                                  c_f32p, c_void_p, c_void_p, c_i64, c_f32p, c_f32p, c_i32p, c_i32p,
+                                  c_int, c_int, c_int, c_int, c_void_p]),
     "gr_score_softmax": (c_int, [c_f32p, c_i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                  c_int, c_int, c_int, c_void_p]),
     "gr_seed_retrieve": (c_int, [c_f32p, c_f32p, c_i64, c_f32p, c_int, c_int, c_int, c_void_p]),

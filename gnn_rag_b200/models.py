@@ -208,12 +208,14 @@ class ReaRev(BaseModel):
         self._get_ent_init(db, rel_f, self.reasoning)           # TypeLayer straight into the h slot
         instructions = self.instruction(db.q_input)              # rearev.py:192-196
         self.dist_history = [db.seed_dist]
-        h = self.reasoning.h_view
+        h = None
         for _t in range(self.num_iter):                          # rearev.py:206-221
             relation_ins = torch.stack(instructions, dim=1)
             dist = db.seed_dist                                  # distribution resets to the seed (:208)
             for j in range(self.num_gnn):                        # only the last layer's h feeds the reform
-                dist, hj = self.reasoning(dist, relation_ins, step=j, need_h=(j == self.num_gnn - 1))
+                # j == 0: the prior is the seed distribution (non-zero on a few nodes) -> sparse-prior path
+                dist, hj = self.reasoning(dist, relation_ins, step=j, need_h=(j == self.num_gnn - 1),
+                                          sparse_prior=(j == 0))
                 h = hj if hj is not None else h
             self.dist_history.append(dist)
             instructions = [getattr(self, "reform" + str(j))(instructions[j], h, db.query_entities, B, N)

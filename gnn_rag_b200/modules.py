@@ -171,6 +171,8 @@ class _GraphLayerBase(nn.Module):
             self.P = _GraphLayerBase._plane_cache[key]
             self.h32 = torch.empty(Nt, D, dtype=torch.float32, device=device)
             self.h32_valid = False
+            self.fr_rows = torch.empty(Nt, dtype=torch.int32, device=device)
+            self.fr_count = torch.zeros(1, dtype=torch.int32, device=device)
             self.dots = torch.empty(2 * Nt, dtype=torch.float32, device=device)
         else:
             self.X = [torch.empty(Nt, Kd, dtype=torch.float32, device=device) for _ in range(2)]
@@ -250,12 +252,35 @@ class ReasonGNNLayer(_GraphLayerBase):
             ti = ops.rel_linear(rel_features_inv, lin.weight, lin.bias, addend=pei, addend_rows=nrel)
             self.tables.append((tf, ti))
 
-    def forward(self, current_dist, relational_ins, step=0, need_h=True):
+    def _forward_sparse_prior(self, current_dist, relational_ins, step, need_h):
+        """Layer whose prior is non-zero on few nodes (csrc/frontier.cu): GEMM over the h segment only for
+        every row, exact recomputation of the frontier rows."""
+        D = self.entity_dim
+        g = self.graph
+        tf, ti = self.tables[step]
+        wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
+        e2e = getattr(self, "e2e_linear" + str(step))
+        sw, sb = self.score_func.weight.view(-1), self.score_func.bias
+        cur, nxt = tuple(self.P[self.cur]), tuple(self.P[1 - self.cur])
+        ops.frontier_rows(g, current_dist, self.fr_rows, self.fr_count)
+        ops.linear_tc_planes(cur[0], cur[1], self.Dp, e2e.weight[:, :D], e2e.bias,
+                             out=self.h32 if need_h else None, out_planes=nxt, w_score=sw, dots=self.dots,
+                             relu=True, k_seg=D, k_seg_pitch=self.Dp)
+        ops.frontier_fixup(g, current_dist, tf, ti, relational_ins, cur, e2e.weight, e2e.bias, sw, nxt,
+                           self.h32 if need_h else None, self.dots, self.fr_rows, self.fr_count, wt, wh)
+        self.h32_valid = bool(need_h)
+        self.cur = 1 - self.cur
+        dist = ops.masked_softmax(self.dots, sb, self.local_entity_mask, self.B, self.N)
+        return dist, (self.h_view if need_h else None)
+
+    def forward(self, current_dist, relational_ins, step=0, need_h=True, sparse_prior=False):
         """One GNN layer (reasongnn.py:134-174): aggregate both directions for every instruction into the
         concat slots, h <- relu(e2e_k([h, nb...])), score, masked softmax.  Returns (dist, h) with h = None when
         ``need_h`` is False (the caller does not read the embeddings of this layer)."""
         D = self.entity_dim
         g = self.graph
+        if sparse_prior and self.use_planes and ops.SPARSE_PRIOR_FASTPATH:
+            return self._forward_sparse_prior(current_dist, relational_ins, step, need_h)
         tf, ti = self.tables[step]
         wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
         if self.use_planes:

@@ -294,6 +294,35 @@ def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=
     return out
 
 
+SPARSE_PRIOR_FASTPATH = True   # first layer of every ReaRev iteration (seed prior): K=1-segment GEMM + frontier fix-up
+
+
+def frontier_rows(g, prior, rows, count):
+    """rows/count <- destination rows with at least one in-edge (either direction) from a node with prior != 0."""
+    prior = _cuda(prior, torch.float32, "prior").contiguous()
+    _lib.check(_L().gr_frontier_rows(_p(g.rowptr_t), _p(g.src_t), _p(g.rowptr_h), _p(g.src_h), _p(prior),
+                                     g.B * g.N, _p(rows), _p(count), _stream()))
+    STATS.launches += 1
+
+
+def frontier_fixup(g, prior, table_fwd, table_inv, ins, cur_planes, W, bias, w_score, nxt_planes, h32, dots,
+                   rows, count, w_t=None, w_h=None):
+    """Recompute the listed rows of one ReaRev layer in full (aggregation + e2e linear + relu + score dot)."""
+    prior = _cuda(prior, torch.float32, "prior").contiguous()
+    ins = _cuda(ins, torch.float32, "ins").contiguous()
+    B, I, D = ins.shape
+    chi, clo = cur_planes
+    nhi, nlo = nxt_planes
+    assert W.stride(1) == 1 and table_fwd.is_contiguous() and table_inv.is_contiguous()
+    rc = _L().gr_frontier_fixup(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t), _p(g.rowptr_h), _p(g.src_h),
+                                _p(g.rel_h), _p(w_h), _p(prior), _p(table_fwd), _p(table_inv), _p(ins),
+                                _p(chi), _p(clo), chi.stride(0), _p(W), W.stride(0), _p(bias), _p(w_score),
+                                _p(nhi), _p(nlo), nhi.stride(0), _p(h32), _p(dots), _p(rows), _p(count),
+                                B, g.N, D, I, _stream())
+    _lib.check(rc)
+    STATS.launches += 1
+
+
 def masked_softmax(dots, b_score, mask, B, N):
     """dist[b,:] = softmax(dots[0,b,:] + dots[1,b,:] + b + (1-mask)*VERY_NEG)  (reasongnn.py:168-169);
     ``dots`` = the [2, B*N] partial score dots of :func:`linear_tc_planes`."""

@@ -170,6 +170,25 @@ int gr_type_layer(const int32_t* rowptr_t, const int32_t* rel_t, const float* w_
                   int B, int N, int D, int64_t F, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Sparse-prior fast path for one ReaRev layer (the first layer of every iteration sees the seed distribution,
+ * rearev.py:208).  Rows none of whose in-edges carries prior mass get exactly zero neighbour messages, so
+ * h_new = relu(W[:, :D] h + b) there (gr_linear_tc_planes with K = one segment).  gr_frontier_rows lists the
+ * other rows (exact for any prior); gr_frontier_fixup recomputes those rows in full -- aggregation of both
+ * directions for every instruction (same edge order/arithmetic as gr_aggregate_dual), e2e linear, relu, score
+ * dot -- and overwrites h_new in the next planes / fp32 h / dots.  list: int32[Nt], count: int32[1] (device).
+ */
+int gr_frontier_rows(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rowptr_h,
+                     const int32_t* src_h, const float* prior, int64_t Nt, int32_t* list, int32_t* count,
+                     void* stream);
+int gr_frontier_fixup(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
+                      const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
+                      const float* prior, const float* table_fwd, const float* table_inv, const float* ins,
+                      const void* cur_hi, const void* cur_lo, int64_t ld_cur, const float* W, int64_t ldw,
+                      const float* bias, const float* w_score, void* nxt_hi, void* nxt_lo, int64_t ld_nxt,
+                      float* h32, float* dots, const int32_t* list, const int32_t* count,
+                      int B, int N, int D, int I, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Scoring: logits[b,n] = dot(h[b,n,:], w_score) + b_score + (1 - mask[b,n]) * (-1e11);
  * dist = softmax_n(logits).  reasongnn.py:165-169 / nsm_gnn.py:67-74.  One CTA per question.
  * h row stride ldh.  mask: float[B*N] (local_entity != num_entity, times possible_tail for NSM

@@ -149,3 +149,29 @@ def test_graphed_step_matches_eager():
         assert torch.equal(dist_g, dist)
         assert float(out.loss) == float(loss)
         assert [r.ent.tolist() for r in ret_g] == [r.ent.tolist() for r in ret_e]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(multi_seed=True, powerlaw=True), dict(n_real="ragged")])
+def test_sparse_prior_fastpath_matches_dense_path(kw):
+    """First layer of every iteration: K=1-segment GEMM + frontier fix-up == full aggregation + full GEMM."""
+    c = dict(S.CONFIGS["cfg2"], B=6, N=700, E=2400)
+    m, args = _model(c)
+    with torch.no_grad():
+        m.reasoning.score_func.weight.mul_(20.0)
+    b = S.make_batch(31, B=c["B"], N=c["N"], E=c["E"], with_weights=False, **kw)
+    outs = {}
+    for flag in (True, False):
+        ops.SPARSE_PRIOR_FASTPATH = flag
+        try:
+            _, _, d, _ = m(b)
+            outs[flag] = (d.clone(), torch.stack(m.dist_history[1:]).clone(), m.reasoning.h_view.clone(),
+                          int(m.reasoning.fr_count.item()))
+        finally:
+            ops.SPARSE_PRIOR_FASTPATH = True
+    rel = ((outs[True][0] - outs[False][0]).abs() / outs[False][0].clamp_min(1e-30)).max().item()
+    assert rel < 1e-4, rel
+    assert (outs[True][2] - outs[False][2]).abs().max().item() <= 1e-4 * outs[False][2].abs().max().item()
+    assert 0 < outs[True][3] < c["B"] * c["N"] // 4 and outs[False][3] == 0
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    _, _, want = O.forward(sd, args, S.WEBQSP_NUM_ENTITY, S.WEBQSP_NUM_WORD, b)
+    assert ((outs[True][0].cpu() - want).abs() / want.clamp_min(1e-30)).max().item() < 1e-3
