@@ -757,7 +757,9 @@ extern "C" int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t l
   __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + t.w_plane_bytes);
   int rc = GR_OK;
-  if (segmented) {
+  if (flags & GR_LINEAR_W_PRESPLIT) {
+    // the caller kept the workspace of an earlier call with the same W / N / K / k_seg / k_seg_pitch
+  } else if (segmented) {
     int64_t work = N * K;
     int grid = (int)std::min<int64_t>(ceil_div(work, 256), 32LL * sm_count());
     split_bf16_seg_kernel<<<grid, 256, 0, stream>>>(W, ldw, N, K, (int)k_seg, (int)k_seg_pitch, w_hi, w_lo, t.kp);

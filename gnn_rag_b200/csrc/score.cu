@@ -93,6 +93,30 @@ __global__ void softmax_kernel(const float* __restrict__ logits, float* __restri
   for (int n = threadIdx.x; n < N; n += blockDim.x) y[n] = expf(x[n] - mx) / s;
 }
 
+// one CTA per question: dist[b,:] = softmax((dots + dots2 + bias) + (1-mask)*VERY_NEG); the logits are staged in
+// dist itself (each thread re-reads only what it wrote)
+__global__ void masked_softmax_kernel(const float* __restrict__ dots, const float* __restrict__ dots2,
+                                      const float* __restrict__ bptr, const float* __restrict__ mask,
+                                      float* __restrict__ dist, int N) {
+  __shared__ float sm[32];
+  const int64_t off = (int64_t)blockIdx.x * N;
+  const float bias = bptr ? bptr[0] : 0.f;
+  float* y = dist + off;
+  float mx = -INFINITY;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float d = dots[off + n];
+    if (dots2) d += dots2[off + n];
+    const float l = (d + bias) + (1.0f - mask[off + n]) * kVeryNeg;
+    y[n] = l;
+    mx = fmaxf(mx, l);
+  }
+  mx = block_reduce(mx, sm, true);
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) s += expf(y[n] - mx);
+  s = block_reduce(s, sm, false);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) y[n] = expf(y[n] - mx) / s;
+}
+
 // one CTA per question; seeds are visited in local-index order (deterministic)
 __global__ void seed_retrieve_kernel(const float* __restrict__ seed, const float* __restrict__ h,
                                      int64_t ldh, float* __restrict__ out, int N, int D) {
@@ -181,12 +205,8 @@ extern "C" int gr_masked_softmax(const float* dots, const float* dots2, const fl
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   GR_CHECK_ARG(dots && mask && dist, "null pointer");
   GR_CHECK_ARG(B > 0 && N > 0, "bad shape");
-  int64_t Nt = (int64_t)B * N;
-  int grid = (int)std::min<int64_t>(ceil_div(Nt, 256), 8LL * sm_count());
-  logits_from_dots_kernel<<<grid, 256, 0, stream>>>(dots, dots2, b_score, mask, dist, Nt);
-  GR_CHECK_LAUNCH();
   int threads = N >= 1024 ? 1024 : (N >= 256 ? 256 : 64);
-  softmax_kernel<<<B, threads, 0, stream>>>(dist, dist, N);
+  masked_softmax_kernel<<<B, threads, 0, stream>>>(dots, dots2, b_score, mask, dist, N);
   GR_CHECK_LAUNCH();
   return GR_OK;
 }

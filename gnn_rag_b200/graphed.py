@@ -72,7 +72,8 @@ class GraphedStep:
         F = int(kb[0].shape[0])
         Q = int(qi.shape[1])
         idx_dtype = torch.int32 if str(kb[0].dtype).endswith("int32") else torch.int64
-        key = (B, N, F, Q, idx_dtype)
+        # parameter versions are part of the key: the captured graph holds pre-formatted (split-bf16) weights
+        key = (B, N, F, Q, idx_dtype, sum(p._version for p in self.model.parameters()))
         ent = self._cache.get(key)
         if ent is None:
             st = self._capture(B, N, F, Q, idx_dtype)

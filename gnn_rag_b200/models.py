@@ -145,6 +145,12 @@ class BaseModel(nn.Module):
             tp = F.kl_div(torch.log(curr_dist + 1e-8), teacher_dist / answer_len, reduction="none")
         return torch.sum(tp * label_valid) / curr_dist.size(0)
 
+    def _loss_and_pred(self, pred_dist, answer_dist):             # rearev.py:228-232 / nsm.py:236-243
+        if self.loss_type == "kl":
+            return ops.kl_loss_pred(pred_dist, answer_dist)
+        case_valid = (torch.sum(answer_dist, dim=1, keepdim=True) > 0).float()
+        return self.calc_loss_label(pred_dist, answer_dist, case_valid), torch.max(pred_dist, dim=1)[1]
+
     def _check_ready(self, training):
         if training:
             raise NotImplementedError(
@@ -182,17 +188,17 @@ class ReaRev(BaseModel):
         self.to(self.device)
 
     def get_rel_feature(self):                                   # rearev.py:91-111
+        """-> ops.RelFeatures with the forward and inverse relation features stacked [2*R1, D]."""
         if self.rel_texts is None:
             lin = self.relation_linear
-            rel = ops.rel_linear(self.relation_embedding.weight, lin.weight, lin.bias)
-            rel_inv = ops.rel_linear(self.relation_embedding_inv.weight, lin.weight, lin.bias)
-            return rel, rel_inv
+            return ops.rel_features_from_embeddings(
+                [self.relation_embedding.weight, self.relation_embedding_inv.weight], lin.weight, lin.bias)
         ins = self.instruction
         rel = ins.question_emb(self.rel_features)
         rel_inv = ins.question_emb(self.rel_features_inv)
         rel = self.self_att_r(rel, (self.rel_texts != ins.pad_val).float())
         rel_inv = self.self_att_r(rel_inv, (self.rel_texts != ins.pad_val).float())
-        return rel.contiguous(), rel_inv.contiguous()
+        return ops.rel_features_from_tensors([rel, rel_inv])
 
     @torch.no_grad()
     def forward(self, batch, training=False):
@@ -203,14 +209,16 @@ class ReaRev(BaseModel):
         db = batching.stage_batch(batch, dev, self.num_relation + 1, self.normalized_gnn, self.norm_rel)
         self.last_batch = db
         B, N = db.B, db.N
-        rel_f, rel_f_inv = self.get_rel_feature()
-        self.reasoning.init_reason(db, rel_f, rel_f_inv)
+        rel_f = self.get_rel_feature()                           # both directions, stacked
+        self.reasoning.init_reason(db, rel_f)
         self._get_ent_init(db, rel_f, self.reasoning)           # TypeLayer straight into the h slot
         instructions = self.instruction(db.q_input)              # rearev.py:192-196
         self.dist_history = [db.seed_dist]
         h = None
+        reforms = [getattr(self, "reform" + str(j)).fusion for j in range(I)]
+        Wr, Wg = [f.r.weight for f in reforms], [f.g.weight for f in reforms]
         for _t in range(self.num_iter):                          # rearev.py:206-221
-            relation_ins = torch.stack(instructions, dim=1)
+            relation_ins = instructions                          # [B, I, D]
             dist = db.seed_dist                                  # distribution resets to the seed (:208)
             for j in range(self.num_gnn):                        # only the last layer's h feeds the reform
                 # j == 0: the prior is the seed distribution (non-zero on a few nodes) -> sparse-prior path
@@ -218,12 +226,10 @@ class ReaRev(BaseModel):
                                           sparse_prior=(j == 0))
                 h = hj if hj is not None else h
             self.dist_history.append(dist)
-            instructions = [getattr(self, "reform" + str(j))(instructions[j], h, db.query_entities, B, N)
-                            for j in range(I)]
+            # all num_ins reforms (seed_retrieve + Fusion) in one launch
+            instructions = ops.query_reform(db.query_entities, h, instructions, Wr, Wg, B, N)
         pred_dist = self.dist_history[-1]
-        case_valid = (torch.sum(db.answer_dist, dim=1, keepdim=True) > 0).float()
-        loss = self.calc_loss_label(pred_dist, db.answer_dist, case_valid)
-        pred = torch.max(pred_dist, dim=1)[1]
+        loss, pred = self._loss_and_pred(pred_dist, db.answer_dist)
         return loss, pred, pred_dist, None
 
 
@@ -256,7 +262,7 @@ class NSM(BaseModel):
 
     def get_rel_feature(self):                                   # nsm.py:97-111
         lin = self.relation_linear1
-        return ops.rel_linear(self.relation_embedding.weight, lin.weight, lin.bias)
+        return ops.rel_features_from_embeddings([self.relation_embedding.weight], lin.weight, lin.bias)
 
     @torch.no_grad()
     def forward(self, batch, training=False):
@@ -271,10 +277,8 @@ class NSM(BaseModel):
         dist = db.seed_dist
         self.dist_history = [dist]
         for i in range(self.num_step):                           # nsm.py:219-222
-            dist = self.reasoning(dist, instruction_list[i], step=i)
+            dist = self.reasoning(dist, instruction_list[:, i], step=i)
             self.dist_history.append(dist)
         pred_dist = self.dist_history[-1]
-        case_valid = (torch.sum(db.answer_dist, dim=1, keepdim=True) > 0).float()
-        loss = self.calc_loss_label(pred_dist, db.answer_dist, case_valid)
-        pred = torch.max(pred_dist, dim=1)[1]
+        loss, pred = self._loss_and_pred(pred_dist, db.answer_dist)
         return loss, pred, pred_dist, None

@@ -33,7 +33,8 @@ class TypeLayer(nn.Module):
         self.norm_rel = norm_rel
 
     def forward(self, graph, rel_features, out, planes=None):
-        table = ops.rel_linear(rel_features, self.kb_self_linear.weight, self.kb_self_linear.bias)
+        """``rel_features``: ops.RelFeatures (only the forward direction is used, layer_init.py:39-41)."""
+        table = ops.rel_table(rel_features, self.kb_self_linear.weight, self.kb_self_linear.bias, dirs=1)[0]
         wt, wh = (graph.wr_t, graph.wr_h) if self.norm_rel else (None, None)
         ops.type_layer(graph, table, out, wt, wh, planes=planes)
         return out
@@ -113,8 +114,12 @@ class LSTMInstruction(nn.Module):
             return hidden
         self.query_node_emb = h_n.squeeze(0).unsqueeze(1)
         self.query_hidden_emb = hidden
-        self.query_mask = (query_text != self.num_word).float()
+        self._query_text = query_text
         return hidden, self.query_node_emb
+
+    @property
+    def query_mask(self):
+        return (self._query_text != self.num_word).float()
 
     def init_reason(self, query_text):
         self.encode_question(query_text)
@@ -130,12 +135,15 @@ class LSTMInstruction(nn.Module):
         return torch.sum(attn * self.query_hidden_emb, dim=1), attn
 
     def forward(self, query_text):
-        self.init_reason(query_text)
-        out = []
-        for i in range(self.num_ins):
-            self.relational_ins, _ = self.get_instruction(self.relational_ins, step=i)
-            out.append(self.relational_ins)
-        return out
+        """-> instructions [B, num_ins, D] (the reference returns the list of its num_ins slices)."""
+        self.encode_question(query_text)
+        I = self.num_ins
+        lins = [getattr(self, "question_linear" + str(i)) for i in range(I)]
+        ins = ops.instructions(self.query_hidden_emb, self.query_node_emb.squeeze(1), query_text, self.num_word,
+                               [l.weight for l in lins], [l.bias for l in lins], self.cq_linear.weight,
+                               self.cq_linear.bias, self.ca_linear.weight.view(-1), self.ca_linear.bias)
+        self.relational_ins = ins[:, I - 1]
+        return ins
 
 
 class _GraphLayerBase(nn.Module):
@@ -233,10 +241,11 @@ class ReasonGNNLayer(_GraphLayerBase):
                 self.add_module("pos_emb_inv" + str(i), nn.Embedding(num_relation, D))
         self.lin_m = nn.Linear(self.num_ins * D, D)           # unused in forward
 
-    def init_reason(self, db, rel_features, rel_features_inv):
+    def init_reason(self, db, rel_features):
         """reasongnn.py:46-58.  Also builds the hoisted per-layer relation tables
-        P_k = rel_linear_k(rel_features) (+ pos_emb_k): 2*num_gnn small GEMMs per forward instead of one
-        Linear over F gathered rows per (iteration, layer, instruction, direction)."""
+        P_k = rel_linear_k(rel_features) (+ pos_emb_k): ONE GEMM per layer over the stacked forward/inverse
+        relation rows per forward, instead of one Linear over F gathered rows per (iteration, layer,
+        instruction, direction)."""
         D = self.entity_dim
         self.graph = db.graph
         self.B, self.N = db.B, db.N
@@ -245,11 +254,10 @@ class ReasonGNNLayer(_GraphLayerBase):
         self.tables = []
         for k in range(self.num_gnn):
             lin = getattr(self, "rel_linear" + str(k))
-            pe = getattr(self, "pos_emb" + str(k)).weight if self.use_posemb else None
-            pei = getattr(self, "pos_emb_inv" + str(k)).weight if self.use_posemb else None
-            nrel = pe.shape[0] if pe is not None else 0
-            tf = ops.rel_linear(rel_features, lin.weight, lin.bias, addend=pe, addend_rows=nrel)
-            ti = ops.rel_linear(rel_features_inv, lin.weight, lin.bias, addend=pei, addend_rows=nrel)
+            add = None
+            if self.use_posemb:
+                add = [getattr(self, "pos_emb" + str(k)).weight, getattr(self, "pos_emb_inv" + str(k)).weight]
+            tf, ti = ops.rel_table(rel_features, lin.weight, lin.bias, addends=add)
             self.tables.append((tf, ti))
 
     def _forward_sparse_prior(self, current_dist, relational_ins, step, need_h):
@@ -315,7 +323,7 @@ class NSMLayer(_GraphLayerBase):
         self.tables = []
         for k in range(self.num_steps):
             lin = getattr(self, "rel_linear" + str(k))
-            self.tables.append(ops.rel_linear(rel_features, lin.weight, lin.bias))
+            self.tables.append(ops.rel_table(rel_features, lin.weight, lin.bias, dirs=1)[0])
         self.possible = torch.empty(db.B * db.N, dtype=torch.float32, device=db.local_entity.device)
         if self.use_planes:
             self.nb32 = torch.empty(db.B * db.N, D, dtype=torch.float32, device=db.local_entity.device)

@@ -2,6 +2,7 @@
 out.  torch is used for device memory and streams only; every op below launches our own sm_100a kernels.
 All ops raise if handed a CPU tensor -- there is no CPU fallback on the product path."""
 import ctypes
+import weakref
 
 import torch
 
@@ -9,6 +10,7 @@ from . import _lib
 
 LINEAR_RELU = 1
 LINEAR_EXACT_FP32 = 2
+LINEAR_W_PRESPLIT = 4
 
 
 class _Stats:
@@ -267,6 +269,59 @@ def split_bf16(A, hi, lo):
     STATS.launches += 1
 
 
+WEIGHT_CACHE = True    # keep the bf16 hi/lo split of a weight matrix until its tensor version changes
+_W_CACHE = {}          # (ptr, ldw, N, K, k_seg, pitch) -> [workspace, version, weakref(base tensor)]
+_P_CACHE = {}          # ptr -> [hi, lo, version, weakref(tensor)]
+
+
+def _base(t):
+    return t._base if t._base is not None else t
+
+
+def _weight_ws(W, N, K, k_seg, k_seg_pitch, nbytes):
+    """Workspace holding W's split planes + whether it is still valid (weight pre-formatting: the conversion
+    runs once per weight VERSION, so an in-place update / load_state_dict re-splits on the next call)."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (W.data_ptr(), W.stride(0), N, K, k_seg, k_seg_pitch)
+    ent = _W_CACHE.get(key) if WEIGHT_CACHE else None
+    if ent is not None and ent[2]() is _base(W) and ent[0].numel() >= nbytes:
+        if ent[1] == W._version:
+            return ent[0], True
+        if not capturing:
+            ent[1] = W._version
+            return ent[0], False          # same buffer, re-split
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    if WEIGHT_CACHE and not capturing:
+        _W_CACHE[key] = [ws, W._version, weakref.ref(_base(W))]
+    return ws, False
+
+
+def param_planes(P):
+    """bf16 hi/lo planes [M, round_up(K, 64)] of a parameter matrix used as a GEMM A operand (relation embedding
+    tables), cached per tensor version like the weight split."""
+    M, K = P.shape
+    capturing = torch.cuda.is_current_stream_capturing()
+    ent = _P_CACHE.get(P.data_ptr()) if WEIGHT_CACHE else None
+    if ent is not None and ent[3]() is P and ent[0].shape[0] == M and ent[2] == P._version:
+        return ent[0], ent[1]
+    if ent is not None and ent[3]() is P and ent[0].shape[0] == M and not capturing:
+        hi, lo = ent[0], ent[1]
+        ent[2] = P._version
+    else:
+        Kp = (K + 63) // 64 * 64
+        hi = torch.zeros(M, Kp, dtype=torch.bfloat16, device=P.device)
+        lo = torch.zeros(M, Kp, dtype=torch.bfloat16, device=P.device)
+        if WEIGHT_CACHE and not capturing:
+            _P_CACHE[P.data_ptr()] = [hi, lo, P._version, weakref.ref(P)]
+    split_bf16(P.detach(), hi, lo)
+    return hi, lo
+
+
+def clear_weight_cache():
+    _W_CACHE.clear()
+    _P_CACHE.clear()
+
+
 def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=None, dots=None, relu=True,
                      k_seg=0, k_seg_pitch=0):
     """tcgen05 split-bf16 GEMM whose A operand already lives in bf16 hi/lo planes [M, >=K].
@@ -282,16 +337,92 @@ def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=
     assert W.stride(1) == 1
     L = _L()
     nbytes = L.gr_linear_tc_planes_workspace_bytes(N, K)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=a_hi.device)
+    ws, presplit = _weight_ws(W, N, K, k_seg, k_seg_pitch, nbytes)
     chi, clo = out_planes if out_planes is not None else (None, None)
+    flags = (LINEAR_RELU if relu else 0) | (LINEAR_W_PRESPLIT if presplit else 0)
     rc = L.gr_linear_tc_planes(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(W), W.stride(0), _p(bias),
                                _p(out), out.stride(0) if out is not None else 0,
                                _p(chi), _p(clo), chi.stride(0) if chi is not None else 0,
                                _p(w_score), _p(dots), M, N, K, k_seg, k_seg_pitch,
-                               LINEAR_RELU if relu else 0, _p(ws), nbytes, _stream())
+                               flags, _p(ws), nbytes, _stream())
     _lib.check(rc)
-    STATS.launches += 2
+    STATS.launches += 1 if presplit else 2
     return out
+
+
+class RelFeatures:
+    """Relation features (ReaRev.get_rel_feature / NSM.get_rel_feature) for all directions, stacked row-wise
+    [n_dir * R1, D]: as split-bf16 planes (A operand of the per-layer relation-table GEMMs) and/or fp32."""
+
+    _buf = {}
+
+    def __init__(self, R1, D, n_dir, device, planes):
+        self.R1, self.D, self.n_dir = R1, D, n_dir
+        self.hi = self.lo = self.f32 = None
+        if planes:
+            Kp = (D + 63) // 64 * 64
+            key = (str(device), n_dir * R1, Kp)
+            if key not in RelFeatures._buf:
+                RelFeatures._buf[key] = (torch.zeros(n_dir * R1, Kp, dtype=torch.bfloat16, device=device),
+                                         torch.zeros(n_dir * R1, Kp, dtype=torch.bfloat16, device=device))
+            self.hi, self.lo = RelFeatures._buf[key]
+        else:
+            self.f32 = torch.empty(n_dir * R1, D, dtype=torch.float32, device=device)
+
+    def rows(self, d):
+        return slice(d * self.R1, (d + 1) * self.R1)
+
+
+def _tc_ok(n_out, k_in):
+    return bool(TC_LINEAR) and 8 <= n_out <= 256 and k_in >= 8
+
+
+def rel_features_from_embeddings(embs, W, bias):
+    """relation_linear applied to the relation embedding table(s) (rearev.py:91-99 / nsm.py:97-104):
+    one tcgen05 GEMM per direction straight into the stacked planes (no fp32 round trip)."""
+    R1, K = embs[0].shape
+    D = W.shape[0]
+    planes = _tc_ok(D, K) and _tc_ok(D, D)
+    rf = RelFeatures(R1, D, len(embs), W.device, planes)
+    for d, E in enumerate(embs):
+        if planes:
+            ahi, alo = param_planes(E)
+            linear_tc_planes(ahi, alo, K, W, bias, out_planes=(rf.hi[rf.rows(d)], rf.lo[rf.rows(d)]), relu=False)
+        else:
+            linear(E, W, bias, out=rf.f32[rf.rows(d)])
+    return rf
+
+
+def rel_features_from_tensors(feats):
+    """Relation features computed elsewhere in fp32 (relation-text encoder, rearev.py:100-111)."""
+    R1, D = feats[0].shape
+    planes = _tc_ok(D, D)
+    rf = RelFeatures(R1, D, len(feats), feats[0].device, planes)
+    for d, f in enumerate(feats):
+        if planes:
+            split_bf16(f.contiguous(), rf.hi[rf.rows(d)], rf.lo[rf.rows(d)])
+        else:
+            rf.f32[rf.rows(d)].copy_(f)
+    return rf
+
+
+def rel_table(rf, W, bias, dirs=None, addends=None):
+    """Hoisted relation projection table(s) = rel_features W^T + b for the stacked directions in ONE GEMM
+    (reasongnn.py:79,105 / nsm_gnn.py:95 / layer_init.py:41 applied to R1 relation rows instead of F facts).
+    Returns the list of per-direction [R1, D] tables.  ``addends``: optional per-direction pos_emb rows."""
+    n = rf.n_dir if dirs is None else dirs
+    rows = n * rf.R1
+    out = torch.empty(rows, W.shape[0], dtype=torch.float32, device=W.device)
+    if rf.hi is not None:
+        linear_tc_planes(rf.hi[:rows], rf.lo[:rows], rf.D, W, bias, out=out, relu=False)
+    else:
+        linear(rf.f32[:rows], W, bias, out=out)
+    tabs = [out[d * rf.R1:(d + 1) * rf.R1] for d in range(n)]
+    if addends is not None:
+        for t, a in zip(tabs, addends):
+            if a is not None:
+                t[: a.shape[0]] += a
+    return tabs
 
 
 SPARSE_PRIOR_FASTPATH = True   # first layer of every ReaRev iteration (seed prior): K=1-segment GEMM + frontier fix-up
@@ -330,7 +461,7 @@ def masked_softmax(dots, b_score, mask, B, N):
     d = dots.view(2, -1)
     _lib.check(_L().gr_masked_softmax(_p(d[0]), _p(d[1]), _p(b_score), _p(mask.contiguous()), _p(dist), B, N,
                                       _stream()))
-    STATS.launches += 2
+    STATS.launches += 1
     return dist
 
 
@@ -354,6 +485,59 @@ def seed_retrieve(seed_info, h, B, N, D):
     _lib.check(_L().gr_seed_retrieve(_p(seed_info), _p(h), h.stride(0), _p(out), B, N, D, _stream()))
     STATS.launches += 1
     return out
+
+
+def _ptr_array(tensors):
+    for t in tensors:
+        _cuda(t, torch.float32, "weight")
+        assert t.is_contiguous()
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def instructions(hidden, qnode, qtext, pad_id, Wq, bq, Wcq, bcq, wca, bca):
+    """All ``num_ins`` instruction vectors of one question batch in one launch (base_encoder.py:73-114).
+    hidden [B,Q,D], qnode [B,D], qtext int64 [B,Q]; Wq/bq: lists of question_linear_i weight/bias.
+    Returns ins [B, I, D]."""
+    hidden = _cuda(hidden, torch.float32, "hidden").contiguous()
+    qnode = _cuda(qnode, torch.float32, "qnode").contiguous()
+    qtext = _cuda(qtext, torch.int64, "qtext").contiguous()
+    B, Q, D = hidden.shape
+    I = len(Wq)
+    out = torch.empty(B, I, D, dtype=torch.float32, device=hidden.device)
+    rc = _L().gr_instructions(_p(hidden), _p(qnode), _p(qtext), int(pad_id), _ptr_array(Wq), _ptr_array(bq),
+                              _p(Wcq.contiguous()), _p(bcq), _p(wca.contiguous()), _p(bca), _p(out), None,
+                              B, Q, D, I, _stream())
+    _lib.check(rc)
+    STATS.launches += 1
+    return out
+
+
+def query_reform(seed_info, h, ins, Wr, Wg, B, N):
+    """ins_new[b,j] = Fusion_j(ins[b,j], seed_info[b] @ h[b]) for every instruction (query_update.py:6-44)."""
+    seed_info = _cuda(seed_info, torch.float32, "seed_info").contiguous()
+    ins = _cuda(ins, torch.float32, "ins").contiguous()
+    h = _cuda(h, torch.float32, "h")
+    assert h.stride(1) == 1
+    _, I, D = ins.shape
+    out = torch.empty_like(ins)
+    rc = _L().gr_query_reform(_p(seed_info), _p(h), h.stride(0), _p(ins), _ptr_array(Wr), _ptr_array(Wg),
+                              _p(out), None, B, N, D, I, _stream())
+    _lib.check(rc)
+    STATS.launches += 1
+    return out
+
+
+def kl_loss_pred(dist, teacher):
+    """-> (loss 0-dim fp32, pred int64[B]) : calc_loss_label('kl') with case_valid, and argmax (base_model.py:186)."""
+    dist = _cuda(dist, torch.float32, "dist").contiguous()
+    teacher = _cuda(teacher, torch.float32, "teacher").contiguous()
+    B, N = dist.shape
+    loss_q = torch.empty(B, dtype=torch.float32, device=dist.device)
+    loss = torch.empty((), dtype=torch.float32, device=dist.device)
+    pred = torch.empty(B, dtype=torch.int64, device=dist.device)
+    _lib.check(_L().gr_kl_loss_pred(_p(dist), _p(teacher), _p(loss_q), _p(loss), _p(pred), B, N, _stream()))
+    STATS.launches += 2
+    return loss, pred
 
 
 def rank_candidates(dist, local_entity, query_entities, pad_id, eps):

@@ -44,6 +44,10 @@ typedef enum gr_status {
 /* flags for gr_linear */
 #define GR_LINEAR_RELU 1u        /* C = relu(A W^T + b)                                      */
 #define GR_LINEAR_EXACT_FP32 2u  /* force the fp32 SIMT kernel (no split-bf16 tensor-core path) */
+#define GR_LINEAR_W_PRESPLIT 4u  /* gr_linear_tc_planes: the workspace still holds the bf16 hi/lo split of the same
+                                  * W (same N, K, k_seg, k_seg_pitch) from an earlier call: skip the conversion pass.
+                                  * For inference with fixed weights (weight pre-formatting, done once per weight
+                                  * version by the caller). */
 
 int gr_abi_version(void);
 const char* gr_last_error(void);
@@ -201,6 +205,33 @@ int gr_score_softmax(const float* h, int64_t ldh, const float* w_score, const fl
  * dots2 != NULL) + b_score + (1-mask)*VERY_NEG. */
 int gr_masked_softmax(const float* dots, const float* dots2, const float* b_score, const float* mask,
                       float* dist, int B, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Question-side updates, one CTA per question (csrc/question.cu).  In the reference each is a chain of 10-20
+ * tiny torch ops on [B, D] tensors; fused here because at B200 speeds they are pure launch latency.
+ * Pointer arrays named *_host are HOST arrays of device pointers (one per instruction, <= 8).
+ *
+ * gr_instructions: LSTMInstruction.forward after the encoder (gnn/modules/question_encoding/
+ * base_encoder.py:73-114): for i < I:  q_i = question_linear_i(qnode);  cq = cq_linear([ri, q_i, q_i-ri, q_i*ri]);
+ * attn = softmax_q(ca_linear(cq * hidden[q]) + (1-mask[q])*VERY_NEG);  ri = sum_q attn[q]*hidden[q];
+ * out[b,i,:] = ri (ri starts at 0).  hidden [B,Q,D], qnode [B,D], qtext int64 [B,Q] (mask = qtext != pad_id).
+ * attn_out optional [B,I,Q]. */
+int gr_instructions(const float* hidden, const float* qnode, const int64_t* qtext, int64_t pad_id,
+                    const float* const* Wq_host, const float* const* bq_host, const float* Wcq,
+                    const float* bcq, const float* wca, const float* bca, float* out, float* attn_out,
+                    int B, int Q, int D, int I, void* stream);
+/* gr_query_reform: the instruction update after every iteration (gnn/models/ReaRev/rearev.py:214-221 ->
+ * QueryReform.forward, gnn/modules/query_update.py:18-44, Fusion :6-16): y = seed_info[b] @ h[b] (seed rows
+ * only, index order); for j < I: z = [x_j, y, x_j - y]; g = sigmoid(G_j z); out_j = g * (R_j z) + (1-g) * x_j.
+ * ins_in/ins_out [B,I,D] (may not alias); Wr/Wg: fusion.r / fusion.g weights [D,3D]; seed_out optional [B,D]. */
+int gr_query_reform(const float* seed_info, const float* h, int64_t ldh, const float* ins_in,
+                    const float* const* Wr_host, const float* const* Wg_host, float* ins_out,
+                    float* seed_out, int B, int N, int D, int I, void* stream);
+/* gr_kl_loss_pred: BaseModel.calc_loss_label with loss_type "kl" (gnn/models/base_model.py:186-215,
+ * rearev.py:156-160,228-232) and pred = argmax_n dist[b,n] (lowest index on ties):
+ * loss = sum_b valid_b * sum_n kl_div(log(dist+1e-8), teacher/len_b) / B.  loss_q: float[B] scratch/output. */
+int gr_kl_loss_pred(const float* dist, const float* teacher, float* loss_q, float* loss, int64_t* pred,
+                    int B, int N, void* stream);
 
 /* seed_retrieve[b,:] = sum_n seed_info[b,n] * h[b,n,:]  (torch.bmm in QueryReform.forward,
  * gnn/modules/query_update.py:40); only rows with seed_info != 0 are read, in index order. */

@@ -21,6 +21,12 @@ def rel_err(a, b, floor=1e-30):
     return ((a - b).abs() / b.abs().clamp_min(floor)).max().item()
 
 
+def max_err(a, b):
+    """max-norm relative error (elementwise relative error is meaningless for entries that cancel to ~0)."""
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
 def assert_ranking_equivalent(got, ref, ref_dist, margin=2e-5):
     """Retrieved lists must equal the reference evaluator's, position by position, except where the item
     we put at a position has a REFERENCE probability within `margin` (relative) of the reference's item at
@@ -280,7 +286,7 @@ def test_type_layer_vs_oracle():
         db = stage(g.batch, g.num_relation + 1, False, g.args["norm_rel"])
         got = torch.from_numpy(g.out["h0"]).view(B * N, D)
         m = build_model(g)
-        rel_f, _ = m.get_rel_feature()
+        rel_f = m.get_rel_feature()
         out = torch.empty(B * N, D, device=DEV)
         m.type_layer(db.graph, rel_f, out)
         assert (out.cpu() - got).abs().max().item() <= TIGHT * (got.abs().max().item() + 1e-12)
@@ -315,6 +321,68 @@ def test_seed_retrieve_vs_bmm():
     want = torch.bmm(seed.unsqueeze(1), h[:, :D].reshape(B, N, D)).squeeze(1)
     assert (got - want).abs().max().item() < 1e-5
     assert (got[3] == 0).all()
+
+
+# ------------------------------------------------------------------ fused question-side kernels -----
+@pytest.mark.parametrize("B,Q,D,I", [(5, 12, 200, 2), (3, 7, 50, 3), (2, 40, 64, 1)])
+def test_instructions_kernel_vs_torch_chain(B, Q, D, I):
+    """gr_instructions == LSTMInstruction.get_instruction applied num_ins times (base_encoder.py:73-114)."""
+    from gnn_rag_b200.modules import LSTMInstruction
+    torch.manual_seed(11)
+    nw = 30
+    emb = torch.nn.Embedding(nw + 1, 16, padding_idx=nw)
+    ins = LSTMInstruction(dict(num_ins=I, entity_dim=D, word_dim=16), emb, nw).to(DEV).eval()
+    text = torch.randint(0, nw, (B, Q), device=DEV)
+    text[0, Q // 2:] = nw                                     # padded tail
+    text[B - 1, :] = nw                                       # all-pad question
+    with torch.no_grad():
+        got = ins(text)                                       # fused kernel
+        ins.init_reason(text)
+        ri, want = ins.relational_ins, []
+        for i in range(I):
+            ri, _ = ins.get_instruction(ri, step=i)
+            want.append(ri)
+        want = torch.stack(want, 1)
+    assert got.shape == (B, I, D)
+    assert max_err(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,D,I", [(4, 700, 200, 2), (3, 1500, 50, 3)])
+def test_query_reform_kernel_vs_torch_modules(B, N, D, I):
+    from gnn_rag_b200.modules import QueryReform
+    torch.manual_seed(12)
+    reforms = [QueryReform(D).to(DEV) for _ in range(I)]
+    h = torch.randn(B * N, D, device=DEV)
+    seed = torch.zeros(B, N, device=DEV)
+    seed[0, 0] = 1.0
+    seed[1, [0, 1, N - 1]] = 1 / 3
+    seed[2, [5, 300, 699]] = torch.tensor([0.2, 0.3, 0.5], device=DEV)   # question 3+ : no seed at all
+    x = torch.randn(B, I, D, device=DEV)
+    with torch.no_grad():
+        got = ops.query_reform(seed, h, x, [r.fusion.r.weight for r in reforms],
+                               [r.fusion.g.weight for r in reforms], B, N)
+        want = torch.stack([reforms[j](x[:, j], h, seed, B, N) for j in range(I)], 1)
+    assert max_err(got, want) < 1e-5
+
+
+def test_kl_loss_pred_kernel_vs_torch():
+    torch.manual_seed(13)
+    B, N = 6, 2000
+    dist = torch.softmax(torch.randn(B, N, device=DEV) * 3, 1)
+    dist[1, 7] = dist[1, 900] = dist[1].max() + 0.1           # tie -> lowest index
+    teacher = torch.zeros(B, N, device=DEV)
+    teacher[0, [3, 4]] = 1.0
+    teacher[1, 10] = 1.0
+    teacher[2, torch.arange(0, N, 7)] = 1.0
+    teacher[4, 1999] = 1.0                                    # questions 3 and 5: no answer -> case_valid 0
+    loss, pred = ops.kl_loss_pred(dist, teacher)
+    m = G.ReaRev.__new__(G.ReaRev)
+    m.loss_type = "kl"
+    valid = (teacher.sum(1, keepdim=True) > 0).float()
+    want = G.models.BaseModel.calc_loss_label(m, dist, teacher, valid)
+    assert abs(loss.item() - want.item()) <= 1e-5 * abs(want.item())
+    assert pred.tolist() == torch.max(dist.cpu(), 1)[1].tolist()
+    assert pred[1].item() == 7
 
 
 # ------------------------------------------------------------------ ranking (bit exact) ------------
