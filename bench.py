@@ -313,13 +313,37 @@ def run_ours(a):
     for _ in range(2):      # warm the host-batch path (allocator, pinned staging)
         e2e_step()
     barrier()
-    t0 = time.perf_counter()
     h2d = d2h = 0
-    for _ in range(a.steps):
-        nb = e2e_step()
-        h2d, d2h = model.last_batch.h2d_bytes, nb
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    if gs is not None:
+        # serving loop: two batches in flight -- submit(i) enqueues the H2D of batch i's inputs (pinned host
+        # memory -> copy stream), the graph and the D2H of its results; collect(i-1) reads batch i-1's candidate
+        # lists on the host.  Every step's H2D and D2H happen inside the timed region; pipeline fill and drain
+        # are inside it too.
+        for _ in range(2):
+            gs.collect(gs.submit(pinned))
+        barrier()
+        t0 = time.perf_counter()
+        prev = None
+        for _ in range(a.steps):
+            tk = gs.submit(pinned)
+            if world > 1:
+                parallel.all_gather_scores(tk.ent.outs[3], B * world)
+            if prev is not None:
+                _ret, d2h, _l, _p = gs.collect(prev)
+            prev = tk
+        _ret, d2h, _l, _p = gs.collect(prev)
+        h2d = model.last_batch.h2d_bytes
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_mode = "pipelined submit/collect, 2 batches in flight"
+    else:
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            nb = e2e_step()
+            h2d, d2h = model.last_batch.h2d_bytes, nb
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_mode = "synchronous"
     # ---- max over ranks ------------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -372,7 +396,7 @@ def run_ours(a):
                 "cuda_graph": bool(a.cuda_graph),
                 "wall_s_timed_region_incl_flush": wall}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "mode": e2e_mode},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if not a.no_cpu_baseline and world == 1:
         sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}

@@ -57,6 +57,8 @@ SIGNATURES = {
     "gr_query_reform": (c_int, [c_f32p, c_f32p, c_i64, c_f32p, c_void_p, c_void_p, c_f32p, c_f32p,
                                 c_int, c_int, c_int, c_int, c_void_p]),
     "gr_kl_loss_pred": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_void_p, c_int, c_int, c_void_p]),
+    "gr_lstm_max_hidden": (c_size, []),
+    "gr_lstm_forward": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_void_p]),
     "gr_seed_retrieve": (c_int, [c_f32p, c_f32p, c_i64, c_f32p, c_int, c_int, c_int, c_void_p]),
     "gr_rank_workspace_bytes": (c_size, [c_int, c_int]),
     "gr_rank_candidates": (c_int, [c_f32p, c_void_p, c_f32p, c_i64, c_dbl, c_i32p, c_i32p, c_i32p,

@@ -21,32 +21,48 @@ constexpr float kVeryNegQ = -100000000000.0f;   // VERY_NEG_NUMBER, base_encoder
 constexpr int kQThreads = 1024;                 // 32 warps: the per-question GEMVs are weight-stream latency bound
 constexpr int kMaxIns = 8;
 
-// y[n] = (bias ? bias[n] : 0) + sum_k W[n*ldw + k] * x[k]  for n in [0, N);  x, y in shared memory.
-// One warp per 4 output rows (lanes across k: coalesced weight reads, 4 independent streams in flight).
-__device__ __forceinline__ void block_gemv(const float* __restrict__ W, int64_t ldw,
-                                           const float* __restrict__ bias, const float* x, float* y, int N,
-                                           int K) {
+// G independent GEMVs of the same shape in one sweep: y[g][n] = (bias[g] ? bias[g][n] : 0) + sum_k W[g][n*ldw + k] * x[g][k]
+// for g < G, n < N;  x[g], y[g] in shared memory.  One warp per 4 output rows of the stacked [G*N] row space (lanes
+// across k: coalesced weight reads, 4 x 4 independent loads in flight per lane), so all 32 warps stay busy even when
+// one GEMV has only D = 200 rows.
+struct GemvGroup {
+  const float* W;
+  const float* bias;
+  const float* x;
+  float* y;
+};
+
+template <int G>
+__device__ __forceinline__ void block_gemv(const GemvGroup (&grp)[G], int ng, int64_t ldw, int N, int K) {
   constexpr int NT = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int n0 = warp * NT; n0 < N; n0 += nw * NT) {
+  const int rows = ng * N;
+  for (int m0 = warp * NT; m0 < rows; m0 += nw * NT) {
     float acc[NT];
     const float* wr[NT];
+    const float* xs[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
+      const int m = min(m0 + t, rows - 1);
+      const int g = m / N, n = m - g * N;
       acc[t] = 0.f;
-      wr[t] = W + (int64_t)min(n0 + t, N - 1) * ldw;
+      wr[t] = grp[g].W + (int64_t)n * ldw;
+      xs[t] = grp[g].x;
     }
 #pragma unroll 4
     for (int k = lane; k < K; k += 32) {
-      const float xv = x[k];
 #pragma unroll
-      for (int t = 0; t < NT; ++t) acc[t] = fmaf(__ldg(wr[t] + k), xv, acc[t]);
+      for (int t = 0; t < NT; ++t) acc[t] = fmaf(__ldg(wr[t] + k), xs[t][k], acc[t]);
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
-      if (lane == 0 && n0 + t < N) y[n0 + t] = acc[t] + (bias ? bias[n0 + t] : 0.f);
+      const int m = m0 + t;
+      if (lane == 0 && m < rows) {
+        const int g = m / N, n = m - g * N;
+        grp[g].y[n] = acc[t] + (grp[g].bias ? grp[g].bias[n] : 0.f);
+      }
     }
   }
 }
@@ -84,7 +100,11 @@ __global__ void __launch_bounds__(kQThreads) instructions_kernel(const InsParams
   }
   for (int q = tid; q < Q; q += blockDim.x) s_mask[q] = p.qtext[(int64_t)b * Q + q] != p.pad ? 1.f : 0.f;
   __syncthreads();
-  for (int i = 0; i < I; ++i) block_gemv(p.Wq[i], D, p.bq[i], s_qn, s_qi + (size_t)i * D, D, D);
+  {
+    GemvGroup grp[kMaxIns];                               // q_i = question_linear_i(qnode) for every i at once
+    for (int i = 0; i < I; ++i) grp[i] = GemvGroup{p.Wq[i], p.bq[i], s_qn, s_qi + (size_t)i * D};
+    block_gemv(grp, I, D, D, D);
+  }
   __syncthreads();
   for (int i = 0; i < I; ++i) {
     const float* qi = s_qi + (size_t)i * D;
@@ -96,7 +116,10 @@ __global__ void __launch_bounds__(kQThreads) instructions_kernel(const InsParams
       s_z[3 * D + d] = q * r;
     }
     __syncthreads();
-    block_gemv(p.Wcq, 4 * D, p.bcq, s_z, s_cq, D, 4 * D);
+    {
+      GemvGroup grp[1] = {GemvGroup{p.Wcq, p.bcq, s_z, s_cq}};
+      block_gemv(grp, 1, 4 * D, D, 4 * D);
+    }
     __syncthreads();
     for (int q = warp; q < Q; q += nw) {                   // ca[q] = ca_linear(cq * hidden[q])
       float s = 0.f;
@@ -151,10 +174,10 @@ __global__ void __launch_bounds__(kQThreads) query_reform_kernel(const ReformPar
   __shared__ int s_woff[kQThreads / 32 + 1];
   const int D = p.D, N = p.N, b = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  float* s_y = smq;            // [D]  seed_retrieve
-  float* s_z = s_y + D;        // [3D]
-  float* s_g = s_z + 3 * D;    // [D]
-  float* s_r = s_g + D;        // [D]
+  float* s_y = smq;            // [D]        seed_retrieve
+  float* s_z = s_y + D;        // [I][3D]
+  float* s_g = s_z + (size_t)p.I * 3 * D;   // [I][D]
+  float* s_r = s_g + (size_t)p.I * D;       // [I][D]
   // ---- seed_retrieve = seed_info[b] @ h[b]  (query_update.py:40); seeds visited in index order ----
   const float* sd = p.seed + (int64_t)b * N;
   float acc = 0.f;             // thread d owns column d (D <= 1024)
@@ -187,23 +210,29 @@ __global__ void __launch_bounds__(kQThreads) query_reform_kernel(const ReformPar
   }
   __syncthreads();
   // ---- Fusion per instruction: z = [x, y, x-y]; g = sigmoid(G z); out = g * (R z) + (1-g) * x ----
-  for (int j = 0; j < p.I; ++j) {
-    const float* x = p.ins_in + ((int64_t)b * p.I + j) * D;
-    for (int d = tid; d < D; d += blockDim.x) {
-      const float xv = x[d], yv = s_y[d];
-      s_z[d] = xv;
-      s_z[D + d] = yv;
-      s_z[2 * D + d] = xv - yv;
+  // (the 2*I GEMVs are independent: one sweep over the stacked rows)
+  for (int i = tid; i < p.I * D; i += blockDim.x) {
+    const int j = i / D, d = i - j * D;
+    const float xv = p.ins_in[((int64_t)b * p.I + j) * D + d], yv = s_y[d];
+    float* z = s_z + (size_t)j * 3 * D;
+    z[d] = xv;
+    z[D + d] = yv;
+    z[2 * D + d] = xv - yv;
+  }
+  __syncthreads();
+  {
+    GemvGroup grp[2 * kMaxIns];
+    for (int j = 0; j < p.I; ++j) {
+      grp[2 * j] = GemvGroup{p.Wg[j], nullptr, s_z + (size_t)j * 3 * D, s_g + (size_t)j * D};
+      grp[2 * j + 1] = GemvGroup{p.Wr[j], nullptr, s_z + (size_t)j * 3 * D, s_r + (size_t)j * D};
     }
-    __syncthreads();
-    block_gemv(p.Wg[j], 3 * D, nullptr, s_z, s_g, D, 3 * D);
-    block_gemv(p.Wr[j], 3 * D, nullptr, s_z, s_r, D, 3 * D);
-    __syncthreads();
-    for (int d = tid; d < D; d += blockDim.x) {
-      const float g = 1.f / (1.f + expf(-s_g[d]));
-      p.ins_out[((int64_t)b * p.I + j) * D + d] = g * s_r[d] + (1.f - g) * s_z[d];
-    }
-    __syncthreads();
+    block_gemv(grp, 2 * p.I, 3 * D, D, 3 * D);
+  }
+  __syncthreads();
+  for (int i = tid; i < p.I * D; i += blockDim.x) {
+    const int j = i / D, d = i - j * D;
+    const float g = 1.f / (1.f + expf(-s_g[i]));
+    p.ins_out[((int64_t)b * p.I + j) * D + d] = g * s_r[i] + (1.f - g) * s_z[(size_t)j * 3 * D + d];
   }
 }
 
@@ -339,7 +368,8 @@ extern "C" int gr_query_reform(const float* seed_info, const float* h, int64_t l
     p.Wg[j] = Wg_host[j];
   }
   p.B = B; p.N = N; p.D = D; p.I = I;
-  const size_t smem = (size_t)6 * D * sizeof(float);
+  const size_t smem = ((size_t)1 + 5 * (size_t)I) * D * sizeof(float);
+  GR_CHECK_ARG(smem <= 48 * 1024, "num_ins x entity_dim too large for shared memory");
   query_reform_kernel<<<B, kQThreads, smem, stream>>>(p);
   GR_CHECK_LAUNCH();
   return GR_OK;
@@ -354,6 +384,138 @@ extern "C" int gr_kl_loss_pred(const float* dist, const float* teacher, float* l
   kl_loss_pred_kernel<<<B, 256, 0, stream>>>(dist, teacher, loss_q, pred, N);
   GR_CHECK_LAUNCH();
   loss_finalize_kernel<<<1, 32, 0, stream>>>(loss_q, loss, B);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gr_lstm_forward: the recurrent half of the question encoder (nn.LSTM, one layer, batch_first, zero initial state;
+// gnn/modules/question_encoding/lstm_encoder.py:27-36).  cuDNN runs it as 2 launches per token (GEMM + cell); here
+// the whole sequence is ONE launch: a cluster of 8 CTAs serves 8 questions, CTA r keeps the W_hh rows of hidden
+// units [r*U, (r+1)*U) (all four gates) resident in shared memory for every time step, computes those units for the
+// cluster's questions and broadcasts the new h slice to the 7 peers through distributed shared memory; one cluster
+// barrier per token.
+// ---------------------------------------------------------------------------------------------------------
+#include <cooperative_groups.h>
+#include <cuda_pipeline.h>
+
+namespace gr {
+namespace {
+namespace cg = cooperative_groups;
+
+constexpr int kLstmCluster = 8;   // CTAs per cluster (portable maximum)
+constexpr int kLstmQB = 8;        // questions per cluster
+constexpr int kLstmThreads = 256;
+
+__global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(kLstmThreads)
+lstm_kernel(const float* __restrict__ gx, const float* __restrict__ Whh, const float* __restrict__ bhh,
+            float* __restrict__ hidden, int B, int Q, int D) {
+  extern __shared__ __align__(16) float sml[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int qb0 = (blockIdx.x / kLstmCluster) * kLstmQB;
+  const int U = (D + kLstmCluster - 1) / kLstmCluster;
+  const int u0 = rank * U;
+  const int nu = max(0, min(U, D - u0));
+  const int pitch = D | 1;                              // odd row pitch: conflict-free row-per-lane reads
+  float* sW = sml;                                      // [4U][pitch]
+  float* sH = reinterpret_cast<float*>(                  // [2][D][QB], 16-byte aligned (float4 reads)
+      (reinterpret_cast<uintptr_t>(sW + (size_t)4 * U * pitch) + 15) & ~(uintptr_t)15);
+  float* sG = sH + (size_t)2 * D * kLstmQB;             // [4U][QB]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 4 * U * D; i += blockDim.x) {   // async copies: all of a thread's loads are in flight at once
+    const int r = i / D, k = i - r * D;
+    const int g = r / U, u = r - g * U;
+    if (u < nu)
+      __pipeline_memcpy_async(sW + (size_t)r * pitch + k, Whh + ((int64_t)g * D + u0 + u) * D + k, sizeof(float));
+    else
+      sW[(size_t)r * pitch + k] = 0.f;
+  }
+  __pipeline_commit();
+  for (int i = tid; i < 2 * D * kLstmQB; i += blockDim.x) sH[i] = 0.f;
+  __pipeline_wait_prior(0);
+  cluster.sync();
+  // gate/cell role: thread -> (hidden unit u, question q); matvec role: thread -> (gate row r, 4 questions)
+  const int gu = tid / kLstmQB, gq = tid % kLstmQB;
+  const bool cell = gu < nu && qb0 + gq < B;
+  const int ug = u0 + gu;
+  const int64_t bq = (int64_t)(qb0 + gq);
+  float c = 0.f;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cell && bhh)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bias[g] = bhh[g * D + ug];
+  const int r = tid & 127, qh = tid >> 7;
+  float gin[4] = {0.f, 0.f, 0.f, 0.f}, gnext[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cell) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) gin[g] = __ldg(gx + (bq * Q) * 4 * D + (int64_t)g * D + ug);
+  }
+  for (int t = 0; t < Q; ++t) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    if (cell && t + 1 < Q) {                             // next token's input projection: a full step of slack
+      const float* gp = gx + (bq * Q + t + 1) * 4 * D + ug;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gnext[g] = __ldg(gp + (int64_t)g * D);
+    }
+    if (r < 4 * U) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* w = sW + (size_t)r * pitch;
+      const float* hb = sH + (size_t)cur * D * kLstmQB + 4 * qh;
+#pragma unroll 4
+      for (int k = 0; k < D; ++k) {
+        const float wv = w[k];
+        const float4 h4 = *reinterpret_cast<const float4*>(hb + (size_t)k * kLstmQB);
+        a0 = fmaf(wv, h4.x, a0);
+        a1 = fmaf(wv, h4.y, a1);
+        a2 = fmaf(wv, h4.z, a2);
+        a3 = fmaf(wv, h4.w, a3);
+      }
+      float* gdst = sG + (size_t)r * kLstmQB + 4 * qh;
+      gdst[0] = a0; gdst[1] = a1; gdst[2] = a2; gdst[3] = a3;
+    }
+    __syncthreads();
+    if (cell) {
+      const float gi = sG[(size_t)(0 * U + gu) * kLstmQB + gq] + gin[0] + bias[0];
+      const float gf = sG[(size_t)(1 * U + gu) * kLstmQB + gq] + gin[1] + bias[1];
+      const float gg = sG[(size_t)(2 * U + gu) * kLstmQB + gq] + gin[2] + bias[2];
+      const float go = sG[(size_t)(3 * U + gu) * kLstmQB + gq] + gin[3] + bias[3];
+      const float iv = 1.f / (1.f + expf(-gi)), fv = 1.f / (1.f + expf(-gf));
+      const float ov = 1.f / (1.f + expf(-go)), gv = tanhf(gg);
+      c = fmaf(fv, c, iv * gv);
+      const float h = ov * tanhf(c);
+      hidden[(bq * Q + t) * D + ug] = h;
+      const size_t off = (size_t)nxt * D * kLstmQB + (size_t)ug * kLstmQB + gq;
+#pragma unroll
+      for (int rk = 0; rk < kLstmCluster; ++rk) cluster.map_shared_rank(sH, rk)[off] = h;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gin[g] = gnext[g];
+    }
+    cluster.sync();                                      // new h visible everywhere; sG / old h free for reuse
+  }
+}
+
+}  // namespace
+}  // namespace gr
+
+extern "C" size_t gr_lstm_max_hidden(void) { return 256; }
+
+extern "C" int gr_lstm_forward(const float* gates_x, const float* W_hh, const float* b_hh, float* hidden, int B,
+                               int Q, int D, void* stream_) {
+  using namespace gr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  GR_CHECK_ARG(gates_x && W_hh && hidden, "null pointer");
+  GR_CHECK_ARG(B > 0 && Q > 0 && D > 0 && D <= 256, "bad shape (hidden size <= 256)");
+  const int U = (D + kLstmCluster - 1) / kLstmCluster;
+  const size_t smem = ((size_t)4 * U * (D | 1) + 8 + (size_t)2 * D * kLstmQB + (size_t)4 * U * kLstmQB) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  GR_CHECK_ARG(smem <= 200 * 1024, "hidden size too large for shared memory");
+  const int clusters = (B + kLstmQB - 1) / kLstmQB;
+  lstm_kernel<<<clusters * kLstmCluster, kLstmThreads, smem, stream>>>(gates_x, W_hh, b_hh, hidden, B, Q, D);
   GR_CHECK_LAUNCH();
   return GR_OK;
 }

@@ -6,6 +6,10 @@ launches.  :class:`GraphedStep` captures the step once per input shape ``(B, N, 
 static device buffers and replays it: per call it only copies the host batch into the static buffers (H2D from
 pinned or pageable memory), replays, and returns views of the static outputs.  Shapes that were not captured yet
 are captured on first use; the numerics are those of the eager path (same kernels, same order).
+
+Serving loop: :meth:`GraphedStep.submit` / :meth:`GraphedStep.collect` pipeline two batches -- the H2D copy of
+batch i+1 (copy stream, into a landing buffer set) and the D2H read of batch i's results overlap the graph of
+batch i, so the end-to-end rate is bounded by the device time of the step, not by device + PCIe time.
 """
 import numpy as np
 import torch
@@ -21,6 +25,11 @@ class _Captured:
     pass
 
 
+class Ticket:
+    """One in-flight step of the submit/collect pipeline."""
+    __slots__ = ("slot", "done", "ent", "local_entity_host", "B", "N")
+
+
 class GraphedStep:
     def __init__(self, model, num_entity, eps=None):
         self.model = model
@@ -28,6 +37,9 @@ class GraphedStep:
         self.eps = model.eps if eps is None else eps
         self.device = next(model.parameters()).device
         self._cache = {}
+        self._copy_stream = None      # H2D stream
+        self._d2h_stream = None       # separate: a D2H waiting for graph i must not block the H2D of batch i+1
+        self._slot = 0
 
     # -- the work that gets captured ------------------------------------------------------------------------
     def _run(self, st):
@@ -66,7 +78,7 @@ class GraphedStep:
         put(st.local_entity, le); put(st.query_entities, qe); put(st.seed_dist, sd); put(st.answer_dist, ad)
         put(st.q_input, qi); put(st.heads, kb[0]); put(st.rels, kb[1]); put(st.tails, kb[2])
 
-    def __call__(self, batch):
+    def _entry(self, batch):
         le, kb, qi = batch[0], batch[2], batch[3]
         B, N = le.shape
         F = int(kb[0].shape[0])
@@ -89,15 +101,110 @@ class GraphedStep:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 outs = self._run(st)
-            ent = (st, g, outs)
+            ent = _Captured()
+            ent.st, ent.g, ent.outs = st, g, outs
+            ent.pipe = None
             self._cache[key] = ent
-        st, g, outs = ent
-        self._fill(st, batch)
-        g.replay()
+        return ent
+
+    def __call__(self, batch):
+        ent = self._entry(batch)
+        self._fill(ent.st, batch)
+        ent.g.replay()
         o = StepOutput()
-        o.db, o.loss, o.pred, o.pred_dist, o.cand_idx, o.cand_count, o.cand_total = outs
+        o.db, o.loss, o.pred, o.pred_dist, o.cand_idx, o.cand_count, o.cand_total = ent.outs
         self.model.last_batch = o.db
         return o
+
+    # -- two-deep pipeline: H2D of batch i+1 and D2H of batch i overlap the graph of batch i -----------------
+    _IN = ("local_entity", "query_entities", "seed_dist", "answer_dist", "q_input", "heads", "rels", "tails")
+
+    def _pipe(self, ent):
+        if ent.pipe is None:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+                self._d2h_stream = torch.cuda.Stream()
+            db, loss, pred, pred_dist, cand_idx, cand_count, _ = ent.outs
+            pipe = _Captured()
+            pipe.land, pipe.out_dev, pipe.out_host = [], [], []
+            pipe.land_free, pipe.done = [], []
+            for _ in range(2):
+                land = _Captured()
+                for name in self._IN:
+                    setattr(land, name, torch.empty_like(getattr(ent.st, name)))
+                pipe.land.append(land)
+                od = dict(cand_idx=torch.empty_like(cand_idx), pred_dist=torch.empty_like(pred_dist),
+                          cand_count=torch.empty_like(cand_count), pred=torch.empty_like(pred),
+                          loss=torch.empty_like(loss))
+                pipe.out_dev.append(od)
+                pipe.out_host.append({k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                                      for k, v in od.items()})
+                pipe.land_free.append(None)
+                pipe.done.append(None)
+            ent.pipe = pipe
+        return ent.pipe
+
+    def submit(self, batch):
+        """Enqueue one step (H2D of ``batch`` on the copy stream, graph replay, async D2H of the results) and
+        return a :class:`Ticket`.  At most two tickets may be outstanding; ``collect`` them in order."""
+        ent = self._entry(batch)
+        pipe = self._pipe(ent)
+        slot, self._slot = self._slot, self._slot ^ 1
+        cs, cur = self._copy_stream, torch.cuda.current_stream()
+        if pipe.done[slot] is not None:
+            pipe.done[slot].synchronize()            # host buffers of this slot have been read out
+        if pipe.land_free[slot] is not None:
+            cs.wait_event(pipe.land_free[slot])
+        land = pipe.land[slot]
+        with torch.cuda.stream(cs):
+            self._fill(land, batch)
+            h2d_done = torch.cuda.Event()
+            h2d_done.record(cs)
+        cur.wait_event(h2d_done)
+        for name in self._IN:                        # landing set -> the graph's static inputs (D2D, ~10 us)
+            getattr(ent.st, name).copy_(getattr(land, name), non_blocking=True)
+        pipe.land_free[slot] = torch.cuda.Event()
+        pipe.land_free[slot].record(cur)
+        ent.g.replay()
+        db, loss, pred, pred_dist, cand_idx, cand_count, _ = ent.outs
+        od = pipe.out_dev[slot]
+        od["cand_idx"].copy_(cand_idx, non_blocking=True)
+        od["pred_dist"].copy_(pred_dist, non_blocking=True)
+        od["cand_count"].copy_(cand_count, non_blocking=True)
+        od["pred"].copy_(pred, non_blocking=True)
+        od["loss"].copy_(loss, non_blocking=True)
+        out_ready = torch.cuda.Event()
+        out_ready.record(cur)
+        ds = self._d2h_stream
+        ds.wait_event(out_ready)
+        with torch.cuda.stream(ds):
+            for k, v in od.items():
+                pipe.out_host[slot][k].copy_(v, non_blocking=True)
+            pipe.done[slot] = torch.cuda.Event()
+            pipe.done[slot].record(ds)
+        self.model.last_batch = db
+        t = Ticket()
+        t.slot, t.done, t.ent = slot, pipe.done[slot], ent
+        le = batch[0]
+        t.local_entity_host = le.cpu().numpy() if isinstance(le, torch.Tensor) else np.asarray(le)
+        t.B, t.N = db.B, db.N
+        return t
+
+    def collect(self, ticket):
+        """Wait for a submitted step and return (retrieved, d2h_bytes, loss, pred): the ordered candidate lists
+        of every question (like :func:`evaluate.retrieve`), the bytes read back, the loss and the argmax."""
+        from .evaluate import Retrieved
+        ticket.done.synchronize()
+        h = ticket.ent.pipe.out_host[ticket.slot]
+        idx_h, dist_h = h["cand_idx"].numpy(), h["pred_dist"].numpy()
+        counts = h["cand_count"].numpy()
+        le = ticket.local_entity_host
+        res = []
+        for b, c in enumerate(counts.tolist()):
+            ix = idx_h[b, :c].astype(np.int64)
+            res.append(Retrieved(ix, le[b, ix].astype(np.int64), dist_h[b, ix]))
+        nbytes = sum(v.numel() * v.element_size() for v in h.values())
+        return res, nbytes, float(h["loss"]), h["pred"].numpy().copy()
 
     def retrieve(self, out):
         """Ordered candidate lists of a :class:`StepOutput` (one D2H), like evaluate.retrieve."""

@@ -107,9 +107,16 @@ class LSTMInstruction(nn.Module):
     def encode_question(self, query_text, store=True):
         emb = self.word_embedding(query_text)
         Bq = query_text.size(0)
-        z = torch.zeros(1, Bq, self.entity_dim, device=emb.device, dtype=emb.dtype)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # keep the encoder fp32-exact
-            hidden, (h_n, c_n) = self.node_encoder(emb, (z, z.clone()))
+        enc = self.node_encoder
+        if emb.is_cuda and self.entity_dim <= ops.LSTM_MAX_HIDDEN:
+            # input projection for all tokens at once (one GEMM), recurrence in one cluster kernel
+            gx = F.linear(emb, enc.weight_ih_l0, enc.bias_ih_l0)
+            hidden = ops.lstm_forward(gx, enc.weight_hh_l0, enc.bias_hh_l0)
+            h_n = hidden[:, -1].unsqueeze(0)
+        else:
+            z = torch.zeros(1, Bq, self.entity_dim, device=emb.device, dtype=emb.dtype)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # keep the encoder fp32-exact
+                hidden, (h_n, c_n) = enc(emb, (z, z.clone()))
         if not store:
             return hidden
         self.query_node_emb = h_n.squeeze(0).unsqueeze(1)

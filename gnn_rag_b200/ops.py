@@ -512,6 +512,22 @@ def instructions(hidden, qnode, qtext, pad_id, Wq, bq, Wcq, bcq, wca, bca):
     return out
 
 
+LSTM_MAX_HIDDEN = 256
+
+
+def lstm_forward(gates_x, W_hh, b_hh):
+    """hidden [B,Q,D] of a one-layer LSTM with zero initial state, given gates_x = x W_ih^T + b_ih [B,Q,4D]
+    (lstm_encoder.py:27-36); one launch for the whole sequence."""
+    gates_x = _cuda(gates_x, torch.float32, "gates_x").contiguous()
+    B, Q, G = gates_x.shape
+    D = G // 4
+    assert W_hh.shape == (4 * D, D) and W_hh.is_contiguous()
+    hidden = torch.empty(B, Q, D, dtype=torch.float32, device=gates_x.device)
+    _lib.check(_L().gr_lstm_forward(_p(gates_x), _p(W_hh), _p(b_hh), _p(hidden), B, Q, D, _stream()))
+    STATS.launches += 1
+    return hidden
+
+
 def query_reform(seed_info, h, ins, Wr, Wg, B, N):
     """ins_new[b,j] = Fusion_j(ins[b,j], seed_info[b] @ h[b]) for every instruction (query_update.py:6-44)."""
     seed_info = _cuda(seed_info, torch.float32, "seed_info").contiguous()

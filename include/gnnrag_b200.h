@@ -233,6 +233,15 @@ int gr_query_reform(const float* seed_info, const float* h, int64_t ldh, const f
 int gr_kl_loss_pred(const float* dist, const float* teacher, float* loss_q, float* loss, int64_t* pred,
                     int B, int N, void* stream);
 
+/* gr_lstm_forward: recurrence of the one-layer LSTM question encoder (gnn/modules/question_encoding/
+ * lstm_encoder.py:27-36: nn.LSTM(batch_first=True), h0 = c0 = 0, gate order i,f,g,o) for all Q tokens in ONE
+ * launch (8-CTA clusters, W_hh slices resident in shared memory, h exchanged through distributed shared memory).
+ * gates_x [B,Q,4D] = x_t W_ih^T + b_ih (computed by the caller); W_hh [4D,D]; b_hh [4D] or NULL;
+ * hidden [B,Q,D] out (h_n = hidden[:, Q-1]).  D <= gr_lstm_max_hidden() (256). */
+size_t gr_lstm_max_hidden(void);
+int gr_lstm_forward(const float* gates_x, const float* W_hh, const float* b_hh, float* hidden, int B, int Q,
+                    int D, void* stream);
+
 /* seed_retrieve[b,:] = sum_n seed_info[b,n] * h[b,n,:]  (torch.bmm in QueryReform.forward,
  * gnn/modules/query_update.py:40); only rows with seed_info != 0 are read, in index order. */
 int gr_seed_retrieve(const float* seed_info, const float* h, int64_t ldh, float* out,

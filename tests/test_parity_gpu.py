@@ -347,6 +347,21 @@ def test_instructions_kernel_vs_torch_chain(B, Q, D, I):
     assert max_err(got, want) < 1e-5
 
 
+@pytest.mark.parametrize("B,Q,D,W", [(64, 12, 200, 300), (5, 7, 50, 16), (9, 30, 256, 64), (3, 4, 33, 8)])
+def test_lstm_cluster_kernel_vs_cudnn(B, Q, D, W):
+    torch.manual_seed(14)
+    lstm = torch.nn.LSTM(input_size=W, hidden_size=D, batch_first=True).to(DEV)
+    x = torch.randn(B, Q, W, device=DEV)
+    with torch.no_grad():
+        z = torch.zeros(1, B, D, device=DEV)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            want, (hn, _) = lstm(x, (z, z.clone()))
+        gx = torch.nn.functional.linear(x, lstm.weight_ih_l0, lstm.bias_ih_l0)
+        got = ops.lstm_forward(gx, lstm.weight_hh_l0, lstm.bias_hh_l0)
+    assert max_err(got, want) < 3e-5        # cuDNN's cell kernel uses its own sigmoid/tanh formulation
+    assert max_err(got[:, -1], hn[0]) < 3e-5
+
+
 @pytest.mark.parametrize("B,N,D,I", [(4, 700, 200, 2), (3, 1500, 50, 3)])
 def test_query_reform_kernel_vs_torch_modules(B, N, D, I):
     from gnn_rag_b200.modules import QueryReform
