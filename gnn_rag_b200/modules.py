@@ -265,14 +265,19 @@ class ReasonGNNLayer(_GraphLayerBase):
             if self.use_posemb:
                 add = [getattr(self, "pos_emb" + str(k)).weight, getattr(self, "pos_emb_inv" + str(k)).weight]
             tf, ti = ops.rel_table(rel_features, lin.weight, lin.bias, addends=add)
-            self.tables.append((tf, ti))
+            pn = None
+            if self.use_planes and ops.aggregate_dual_abs_supported(db.N, D, self.Dp, tf.shape[0]):
+                # tf / ti are the two halves of one stacked [2*R1, D] matrix: one conversion launch for both
+                pn_all = ops.pad_table256(tf._base if tf._base is not None else torch.cat([tf, ti]))
+                pn = (pn_all[: tf.shape[0]], pn_all[tf.shape[0]:])
+            self.tables.append((tf, ti, pn))
 
     def _forward_sparse_prior(self, current_dist, relational_ins, step, need_h):
         """Layer whose prior is non-zero on few nodes (csrc/frontier.cu): GEMM over the h segment only for
         every row, exact recomputation of the frontier rows."""
         D = self.entity_dim
         g = self.graph
-        tf, ti = self.tables[step]
+        tf, ti, _pn = self.tables[step]
         wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
         e2e = getattr(self, "e2e_linear" + str(step))
         sw, sb = self.score_func.weight.view(-1), self.score_func.bias
@@ -296,9 +301,12 @@ class ReasonGNNLayer(_GraphLayerBase):
         g = self.graph
         if sparse_prior and self.use_planes and ops.SPARSE_PRIOR_FASTPATH:
             return self._forward_sparse_prior(current_dist, relational_ins, step, need_h)
-        tf, ti = self.tables[step]
+        tf, ti, pn = self.tables[step]
         wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
-        if self.use_planes:
+        if self.use_planes and pn is not None and ops.AGG_ABS:
+            ops.aggregate_dual_abs(g, current_dist, pn[0], pn[1], relational_ins, self.cur_planes(), self.Dp,
+                                  self.Dp, wt, wh)
+        elif self.use_planes:
             ops.aggregate_dual(g, current_dist, tf, ti, relational_ins, None, self.Dp, wt, wh,
                                planes=self.cur_planes(), seg_pitch=self.Dp)
         else:

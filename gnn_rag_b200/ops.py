@@ -244,6 +244,41 @@ def aggregate_dual(g, prior, table_fwd, table_inv, ins, out, out_col0, w_t=None,
     return out
 
 
+AGG_ABS = True          # |v|-accumulating aggregation kernel (csrc/aggregate_abs.cu) for the shapes it specialises
+
+
+def pad_table256(table):
+    """[rows, D] fp32 relation table -> zero-padded [rows, 256] copy (1 KB rows: every lane of the gather is
+    in-bounds) for :func:`aggregate_dual_abs`."""
+    table = _cuda(table, torch.float32, "table")
+    rows, D = table.shape
+    assert table.stride(1) == 1
+    pn = torch.empty(rows, 256, dtype=torch.float32, device=table.device)
+    _lib.check(_L().gr_pad_table256(_p(table), table.stride(0), rows, D, _p(pn), _stream()))
+    STATS.launches += 1
+    return pn
+
+
+def aggregate_dual_abs_supported(N, D, seg_pitch, R1):
+    return bool(AGG_ABS) and bool(_L().gr_aggregate_dual_abs_supported(N, D, seg_pitch, R1))
+
+
+def aggregate_dual_abs(g, prior, pn_fwd, pn_inv, ins, planes, out_col0, seg_pitch, w_t=None, w_h=None):
+    """Both directions of one ReaRev layer into the split-bf16 planes, |v|-accumulating kernel (reasongnn.py:150-161)."""
+    prior = _cuda(prior, torch.float32, "prior").contiguous()
+    ins = _cuda(ins, torch.float32, "ins").contiguous()
+    B, I, D = ins.shape
+    hi, lo = planes
+    assert pn_fwd.is_contiguous() and pn_inv.is_contiguous() and hi.stride(0) == lo.stride(0)
+    with _AggTimer(("dual", I)):
+        rc = _L().gr_aggregate_dual_abs(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t),
+                                       _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(w_h),
+                                       _p(prior), _p(pn_fwd), _p(pn_inv), _p(ins), _p(hi), _p(lo), hi.stride(0),
+                                       out_col0, seg_pitch, B, g.N, D, I, g.F, _stream())
+    _lib.check(rc)
+    STATS.launches += (I + 3) // 4
+
+
 def type_layer(g, table, out, w_t=None, w_h=None, planes=None):
     """out[:, :D] = relu(sum_tail w*table[rel] + sum_head w*table[rel]) (layer_init.py:46-57); optional
     split-bf16 planes of the same values."""

@@ -53,7 +53,8 @@ int gr_abi_version(void);
 const char* gr_last_error(void);
 /* runtime switches: "agg_tma" (0|1: stage CSR slices with bulk TMA copies), "linear_tc" (0|1: split-bf16
  * tcgen05 GEMM for gr_linear when the shape allows), "tc_cluster" (1|2: CTAs per cluster that share the W
- * tiles of the tcgen05 GEMM through TMA multicast).  Process-wide; set before launching work. */
+ * tiles of the tcgen05 GEMM through TMA multicast), "agg_abs_minb" (2|3: CTAs per SM the |v| aggregation kernel is
+ * compiled for).  Process-wide; set before launching work. */
 int gr_set_option(const char* name, int64_t value);
 static inline int64_t gr_pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
 
@@ -162,6 +163,21 @@ int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, const int32
                       float* out, int64_t out_row_stride, int64_t out_col0, int64_t seg_pitch,
                       void* out_hi, void* out_lo, int64_t ld_planes,
                       int B, int N, int D, int I, int64_t F, void* stream);
+
+/* Specialised variant of gr_aggregate_dual for the hot shape (csrc/aggregate_abs.cu).  The hoisted relation table is
+ * copied once per layer into a zero-padded 256-column layout (gr_pad_table256: table [rows, D] fp32, row stride ldt
+ * -> out [rows][256] fp32, 16-byte aligned) so every lane of the gather is in-bounds, and the edge loop accumulates
+ * sum c*v and sum c*|v| (|.| is a free FFMA2 source modifier on sm_100) instead of taking relu of every gathered
+ * element: sum c*relu(+-v) = (Q +- S)/2.  Output: the split-bf16 planes only.  This build specialises D = 200,
+ * seg_pitch = 208, N >= 64 (gr_aggregate_dual_abs_supported); other shapes use gr_aggregate_dual.
+ * Same reference lines: reasongnn.py:61-116. */
+int gr_pad_table256(const float* table, int64_t ldt, int64_t rows, int D, float* pn, void* stream);
+int gr_aggregate_dual_abs_supported(int N, int D, int64_t seg_pitch, int64_t R1);
+int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
+                         const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
+                         const float* prior, const float* pn_fwd, const float* pn_inv, const float* ins,
+                         void* out_hi, void* out_lo, int64_t ld_planes, int64_t out_col0, int64_t seg_pitch,
+                         int B, int N, int D, int I, int64_t F, void* stream);
 
 /* Diagnostic only (scripts/agg_probe.py): replays the aggregation kernel's store pattern without any edge work. */
 int gr_debug_store_probe(void* hi, void* lo, int64_t Nt, int64_t ld, int col_start, int ncols, int mode,

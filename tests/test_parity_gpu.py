@@ -278,6 +278,51 @@ def test_aggregate_deterministic_and_tma_identical():
     assert torch.equal(outs[0], outs[2])          # TMA-staged variant bit identical to plain staging
 
 
+@pytest.mark.parametrize("I,minb,normalized", [(2, 3, False), (2, 2, True), (1, 3, False), (3, 3, True), (5, 2, False)])
+def test_aggregate_abs_kernel_matches_generic_kernel(I, minb, normalized):
+    """|v|-accumulating aggregation (csrc/aggregate_abs.cu) == the generic kernel's planes:
+    hubs that overflow the staged edge slice, ragged questions, edge weights, a one-hot prior (zero rows exact),
+    I > 4 (two launches), both occupancy builds.  Run-to-run bit identical."""
+    B, N, D, R = 5, 700, 200, 60
+    b = S.make_batch(41, B=B, N=N, E=5000, num_entity=5000, num_relation=R, num_word=50, n_real="ragged",
+                     powerlaw=True)
+    db = stage(b, R + 1, normalized=normalized)
+    g = db.graph
+    wt, wh = (g.w_t, g.w_h) if normalized else (None, None)
+    rs = np.random.RandomState(2)
+    tab = torch.from_numpy(rs.randn(2 * (R + 1), D).astype(np.float32)).to(DEV)
+    tab[3].abs_()                                            # a non-negative table row
+    tf, ti = tab[: R + 1], tab[R + 1:]
+    ins = torch.from_numpy(rs.randn(B, I, D).astype(np.float32)).to(DEV)
+    pn = ops.pad_table256(tab)
+    pf, pi = pn[: R + 1], pn[R + 1:]
+    assert ops.aggregate_dual_abs_supported(N, D, 208, R + 1)
+    Kp = (208 * (2 * I + 1) + 63) // 64 * 64
+    ops.set_option("agg_abs_minb", minb)
+    try:
+        for kind in ("dense", "onehot"):
+            prior = (torch.softmax(torch.from_numpy(rs.randn(B, N).astype(np.float32)), 1) if kind == "dense"
+                     else torch.from_numpy(b[4].astype(np.float32))).to(DEV)
+            ref = [torch.full((B * N, Kp), 7.0, dtype=torch.bfloat16, device=DEV) for _ in range(2)]
+            ops.aggregate_dual(g, prior, tf, ti, ins, None, 208, wt, wh, planes=tuple(ref), seg_pitch=208)
+            outs = []
+            for _ in range(2):
+                got = [torch.full((B * N, Kp), 7.0, dtype=torch.bfloat16, device=DEV) for _ in range(2)]
+                ops.aggregate_dual_abs(g, prior, pf, pi, ins, tuple(got), 208, 208, wt, wh)
+                outs.append(got)
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+            got = outs[0]
+            assert (got[0][:, :208] == 7.0).all()            # the h segment is not touched
+            a = got[0][:, 208:208 * (2 * I + 1)].float() + got[1][:, 208:208 * (2 * I + 1)].float()
+            r = ref[0][:, 208:208 * (2 * I + 1)].float() + ref[1][:, 208:208 * (2 * I + 1)].float()
+            assert (a - r).abs().max().item() <= 2e-5 * r.abs().max().item()   # two hi+lo roundings of ~2^-18 each
+            assert ((r == 0) <= (a == 0)).all()               # exact zeros stay exact zeros
+            seg = a.view(B * N, 2 * I, 208)
+            assert (seg[:, :, 200:] == 0).all()               # padding columns written as zeros
+    finally:
+        ops.set_option("agg_abs_minb", 3)
+
+
 def test_type_layer_vs_oracle():
     for name in ("rearev_small", "rearev_norm"):
         g = Golden(name)
