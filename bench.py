@@ -52,8 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agg-tma", type=int, default=None)
     ap.add_argument("--agg-abs", type=int, default=None, help="0: generic aggregation kernel instead of the |v|-accumulating one")
-    ap.add_argument("--agg-abs-eb", type=int, default=None, help="2|4 gathered edges per block")
-    ap.add_argument("--agg-abs-minb", type=int, default=None, help="2|3 CTAs/SM build of the |v|-accumulating kernel")
+    ap.add_argument("--agg-abs-ws", type=int, default=None, help="0: one CTA per tile instead of the persistent kernel")
     ap.add_argument("--tc-bk", type=int, default=None)
     ap.add_argument("--tc-cluster", type=int, default=None)
     ap.add_argument("--cuda-graph", type=int, default=1,
@@ -220,10 +219,8 @@ def run_ours(a):
         ops.set_option("agg_tma", a.agg_tma)
     if a.agg_abs is not None:
         ops.AGG_ABS = bool(a.agg_abs)
-    if a.agg_abs_minb is not None:
-        ops.set_option("agg_abs_minb", a.agg_abs_minb)
-    if a.agg_abs_eb is not None:
-        ops.set_option("agg_abs_eb", a.agg_abs_eb)
+    if a.agg_abs_ws is not None:
+        ops.set_option("agg_abs_ws", a.agg_abs_ws)
     if a.tc_bk is not None:
         ops.set_option("tc_bk", a.tc_bk)
     if a.tc_cluster is not None:

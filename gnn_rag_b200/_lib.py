@@ -39,7 +39,7 @@ SIGNATURES = {
     "gr_aggregate_dual_abs_supported": (c_int, [c_int, c_int, c_i64, c_i64]),
     "gr_aggregate_dual_abs": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p,
                                      c_f32p, c_f32p, c_f32p, c_f32p, c_void_p, c_void_p, c_i64, c_i64, c_i64,
-                                     c_int, c_int, c_int, c_int, c_i64, c_void_p]),
+                                     c_int, c_int, c_int, c_int, c_i64, c_i32p, c_void_p]),
     "gr_debug_store_probe": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_void_p]),
     "gr_type_layer": (c_int, [c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_i64,
                               c_void_p, c_void_p, c_i64,

@@ -263,6 +263,9 @@ def aggregate_dual_abs_supported(N, D, seg_pitch, R1):
     return bool(AGG_ABS) and bool(_L().gr_aggregate_dual_abs_supported(N, D, seg_pitch, R1))
 
 
+_TILE_COUNTER = {}
+
+
 def aggregate_dual_abs(g, prior, pn_fwd, pn_inv, ins, planes, out_col0, seg_pitch, w_t=None, w_h=None):
     """Both directions of one ReaRev layer into the split-bf16 planes, |v|-accumulating kernel (reasongnn.py:150-161)."""
     prior = _cuda(prior, torch.float32, "prior").contiguous()
@@ -270,11 +273,14 @@ def aggregate_dual_abs(g, prior, pn_fwd, pn_inv, ins, planes, out_col0, seg_pitc
     B, I, D = ins.shape
     hi, lo = planes
     assert pn_fwd.is_contiguous() and pn_inv.is_contiguous() and hi.stride(0) == lo.stride(0)
+    dev = prior.device
+    if dev not in _TILE_COUNTER:
+        _TILE_COUNTER[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
     with _AggTimer(("dual", I)):
         rc = _L().gr_aggregate_dual_abs(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t),
                                        _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(w_h),
                                        _p(prior), _p(pn_fwd), _p(pn_inv), _p(ins), _p(hi), _p(lo), hi.stride(0),
-                                       out_col0, seg_pitch, B, g.N, D, I, g.F, _stream())
+                                       out_col0, seg_pitch, B, g.N, D, I, g.F, _p(_TILE_COUNTER[dev]), _stream())
     _lib.check(rc)
     STATS.launches += (I + 3) // 4
 

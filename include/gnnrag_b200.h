@@ -53,8 +53,8 @@ int gr_abi_version(void);
 const char* gr_last_error(void);
 /* runtime switches: "agg_tma" (0|1: stage CSR slices with bulk TMA copies), "linear_tc" (0|1: split-bf16
  * tcgen05 GEMM for gr_linear when the shape allows), "tc_cluster" (1|2: CTAs per cluster that share the W
- * tiles of the tcgen05 GEMM through TMA multicast), "agg_abs_minb" (2|3: CTAs per SM the |v| aggregation kernel is
- * compiled for).  Process-wide; set before launching work. */
+ * tiles of the tcgen05 GEMM through TMA multicast), "agg_abs_ws" (0|1: persistent warp-specialised build of the |v| aggregation
+ * kernel).  Process-wide; set before launching work. */
 int gr_set_option(const char* name, int64_t value);
 static inline int64_t gr_pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
 
@@ -177,7 +177,10 @@ int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src_t, const i
                          const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
                          const float* prior, const float* pn_fwd, const float* pn_inv, const float* ins,
                          void* out_hi, void* out_lo, int64_t ld_planes, int64_t out_col0, int64_t seg_pitch,
-                         int B, int N, int D, int I, int64_t F, void* stream);
+                         int B, int N, int D, int I, int64_t F, int32_t* tile_counter, void* stream);
+/* tile_counter: 4 bytes of device scratch (zeroed by the call) -> the persistent, warp-specialised kernel (a producer
+ * warp stages the next 64-row tile while eight consumer warps aggregate the current one; dynamic tile scheduler);
+ * NULL -> one CTA per tile. */
 
 /* Diagnostic only (scripts/agg_probe.py): replays the aggregation kernel's store pattern without any edge work. */
 int gr_debug_store_probe(void* hi, void* lo, int64_t Nt, int64_t ld, int col_start, int ncols, int mode,

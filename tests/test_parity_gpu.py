@@ -278,11 +278,12 @@ def test_aggregate_deterministic_and_tma_identical():
     assert torch.equal(outs[0], outs[2])          # TMA-staged variant bit identical to plain staging
 
 
-@pytest.mark.parametrize("I,minb,normalized", [(2, 3, False), (2, 2, True), (1, 3, False), (3, 3, True), (5, 2, False)])
-def test_aggregate_abs_kernel_matches_generic_kernel(I, minb, normalized):
+@pytest.mark.parametrize("ws", [1, 0])
+@pytest.mark.parametrize("I,normalized", [(2, False), (2, True), (1, False), (3, True), (5, False)])
+def test_aggregate_abs_kernel_matches_generic_kernel(I, normalized, ws):
     """|v|-accumulating aggregation (csrc/aggregate_abs.cu) == the generic kernel's planes:
     hubs that overflow the staged edge slice, ragged questions, edge weights, a one-hot prior (zero rows exact),
-    I > 4 (two launches), both occupancy builds.  Run-to-run bit identical."""
+    I > 4 (two launches), persistent and one-CTA-per-tile builds.  Run-to-run bit identical."""
     B, N, D, R = 5, 700, 200, 60
     b = S.make_batch(41, B=B, N=N, E=5000, num_entity=5000, num_relation=R, num_word=50, n_real="ragged",
                      powerlaw=True)
@@ -298,7 +299,7 @@ def test_aggregate_abs_kernel_matches_generic_kernel(I, minb, normalized):
     pf, pi = pn[: R + 1], pn[R + 1:]
     assert ops.aggregate_dual_abs_supported(N, D, 208, R + 1)
     Kp = (208 * (2 * I + 1) + 63) // 64 * 64
-    ops.set_option("agg_abs_minb", minb)
+    ops.set_option("agg_abs_ws", ws)       # persistent warp-specialised kernel / one CTA per tile
     try:
         for kind in ("dense", "onehot"):
             prior = (torch.softmax(torch.from_numpy(rs.randn(B, N).astype(np.float32)), 1) if kind == "dense"
@@ -320,7 +321,7 @@ def test_aggregate_abs_kernel_matches_generic_kernel(I, minb, normalized):
             seg = a.view(B * N, 2 * I, 208)
             assert (seg[:, :, 200:] == 0).all()               # padding columns written as zeros
     finally:
-        ops.set_option("agg_abs_minb", 3)
+        ops.set_option("agg_abs_ws", 1)
 
 
 def test_type_layer_vs_oracle():
