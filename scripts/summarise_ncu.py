@@ -4,6 +4,9 @@ import collections, csv, io, json, subprocess, sys
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_st.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.avg.per_cycle_active",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
@@ -49,6 +52,7 @@ def launch_summary(csv_path, nfwd):
         v = v / 1e3 if r["Metric Unit"] == "ns" else (v * 1e3 if r["Metric Unit"] == "ms" else v)
         agg[key][0] += 1
         agg[key][1] += v
+    nfwd = max(1, sum(1 for r in rows if "hist_kernel" in r["Kernel Name"]))   # one CSR build per forward
     tot = sum(v[1] for v in agg.values())
     ours = sum(v[1] for k, v in agg.items() if k.startswith("ours"))
     lines = ["# per-kernel device time, %d forwards (ncu --metrics gpu__time_duration.sum --clock-control none;" % nfwd,
@@ -63,12 +67,12 @@ def launch_summary(csv_path, nfwd):
 if __name__ == "__main__":
     tag = sys.argv[1]
     open("profiles/%s_launches.txt" % tag, "w").write(launch_summary("gpurun_out/launches_%s.csv" % tag, 5))
-    t, d = full_summary("gpurun_out/agg_%s.ncu-rep" % tag, "aggregation kernel (gr_aggregate_dual), launch 0 = one-hot seed prior, launch 1 = dense prior; cfg2")
+    t, d = full_summary("gpurun_out/agg_%s.ncu-rep" % tag, "aggregation kernel (gr_aggregate_dual_abs, persistent warp-specialised), two dense-prior launches (layers 1 and 2 of iteration 0); cfg2")
     open("profiles/%s_agg_kernel.txt" % tag, "w").write(t)
     traffic = [(float(x["dram__bytes_read.sum"]) + float(x["dram__bytes_write.sum"])) * 1e6 for x in d]
     t2, d2 = full_summary("gpurun_out/tc_%s.ncu-rep" % tag, "tcgen05 e2e GEMM (gr_linear_tc_planes), cfg2: M=128000 N=200 K=1040")
     open("profiles/%s_tc_gemm.txt" % tag, "w").write(t2)
-    json.dump({"agg_dense_traffic_bytes_per_launch": traffic[1], "agg_seed_traffic_bytes_per_launch": traffic[0],
-               "agg_dense_ncu_us": float(d[1]["gpu__time_duration.sum"]), "source": "profiles/%s_agg_kernel.txt" % tag},
+    json.dump({"agg_dense_traffic_bytes_per_launch": traffic[-1],
+               "agg_dense_ncu_us": float(d[-1]["gpu__time_duration.sum"]), "source": "profiles/%s_agg_kernel.txt" % tag},
               open("profiles/%s_traffic.json" % tag, "w"), indent=1)
     print(open("profiles/%s_launches.txt" % tag).read()[:2500]); print(t); print(t2)
