@@ -79,6 +79,13 @@ __device__ __forceinline__ void fma4_abs(float4& acc, float c, const float4& v) 
   acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
+__device__ __forceinline__ float4 addsub4(const float4& q, const float4& s, float sign) {   // q + sign*s, packed
+  const float2 ss = make_float2(sign, sign);
+  const float2 lo = __ffma2_rn(make_float2(s.x, s.y), ss, make_float2(q.x, q.y));
+  const float2 hi = __ffma2_rn(make_float2(s.z, s.w), ss, make_float2(q.z, q.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // y = xp*(Q+S) + xn*(Q-S)  (xp, xn already carry the 1/2) -> (hi, lo) bf16 pairs, 8-byte stores into both planes
 __device__ __forceinline__ void emit4(__nv_bfloat16* ph, __nv_bfloat16* pl, bool pred, const float4& xp,
                                       const float4& xn, const float4& U, const float4& V) {
@@ -88,8 +95,10 @@ __device__ __forceinline__ void emit4(__nv_bfloat16* ph, __nv_bfloat16* pl, bool
   y23 = __ffma2_rn(make_float2(xn.z, xn.w), make_float2(V.z, V.w), y23);
   const __nv_bfloat162 h01 = __floats2bfloat162_rn(y01.x, y01.y), h23 = __floats2bfloat162_rn(y23.x, y23.y);
   const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-  const __nv_bfloat162 l01 = __floats2bfloat162_rn(y01.x - f01.x, y01.y - f01.y);
-  const __nv_bfloat162 l23 = __floats2bfloat162_rn(y23.x - f23.x, y23.y - f23.y);
+  const float2 m1 = make_float2(-1.f, -1.f);
+  const float2 r01 = __ffma2_rn(f01, m1, y01), r23 = __ffma2_rn(f23, m1, y23);   // y - hi, exact, packed
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(r01.x, r01.y);
+  const __nv_bfloat162 l23 = __floats2bfloat162_rn(r23.x, r23.y);
   if (pred) {
     *reinterpret_cast<uint2*>(ph) =
         make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
@@ -150,10 +159,8 @@ __device__ __forceinline__ void row_unit(const int2* __restrict__ rc, int beg, i
     const float4 v1 = ld1 ? ldg4(a + 512) : zero4();
     fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
   }
-  const float4 U0 = make_float4(Q0.x + S0.x, Q0.y + S0.y, Q0.z + S0.z, Q0.w + S0.w);   // 2 * sum c*relu(v)
-  const float4 V0 = make_float4(Q0.x - S0.x, Q0.y - S0.y, Q0.z - S0.z, Q0.w - S0.w);   // 2 * sum c*relu(-v)
-  const float4 U1 = make_float4(Q1.x + S1.x, Q1.y + S1.y, Q1.z + S1.z, Q1.w + S1.w);
-  const float4 V1 = make_float4(Q1.x - S1.x, Q1.y - S1.y, Q1.z - S1.z, Q1.w - S1.w);
+  const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);   // 2 * sum c*relu(v), 2 * sum c*relu(-v)
+  const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
 #pragma unroll
   for (int j = 0; j < NI; ++j) {
     const int seg = seg_d + j * 2 * SEGP;
