@@ -35,6 +35,38 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert sorted(_lib.SIGNATURES) == syms
 
 
+def declared_arities():
+    """name -> number of parameters of every prototype in the header."""
+    text = open(os.path.join(ROOT, "include", "gnnrag_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(gr_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        out[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_ctypes_signatures_have_the_header_arity():
+    """A drifted binding (argument added on one side only) would scramble the stack silently."""
+    ar = declared_arities()
+    for name, (_res, argtypes) in _lib.SIGNATURES.items():
+        assert name in ar, name
+        assert len(argtypes) == ar[name], "%s: header has %d parameters, ctypes binding %d" % (
+            name, ar[name], len(argtypes))
+
+
+def test_new_entry_points_validate_arguments():
+    lib = _lib.load()
+    assert lib.gr_aggregate_dual_abs_supported(2000, 200, 208, 6107) == 1
+    assert lib.gr_aggregate_dual_abs_supported(2000, 64, 64, 100) == 0        # other shapes: generic kernel
+    assert lib.gr_aggregate_dual_abs_supported(32, 200, 208, 100) == 0        # N < one tile
+    assert lib.gr_lstm_max_hidden() == 256
+    assert lib.gr_lstm_forward(None, None, None, None, 1, 1, 8, None) == -1
+    assert lib.gr_pad_table256(None, 0, 1, 8, None, None) == -1
+    assert lib.gr_kl_loss_pred(None, None, None, None, None, 1, 1, None) == -1
+    assert lib.gr_frontier_rows(None, None, None, None, None, 1, None, None, None) == -1
+
+
 def test_argument_validation_returns_status_codes():
     lib = _lib.load()
     rc = lib.gr_linear(None, 4, None, 4, None, None, 0, 0, None, 4, 4, 4, 4, 0, None)

@@ -104,3 +104,21 @@ def test_all_gather_scores_gloo_world2(B):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm) runs without a GPU and prints ONE JSON line with the
+    contract keys; it times the oracle port of the reference op sequence on the host cores."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] and line["unit"] == "questions/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"]
