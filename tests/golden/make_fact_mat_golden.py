@@ -1,7 +1,7 @@
 """Golden outputs of the UNMODIFIED reference ``BasicDataLoader._build_fact_mat`` (gnn/dataset_load.py:473-527) on
 the stand-in loader states of tests/loader_fixture.py.  Run in the build container (needs /root/reference):
     python tests/golden/make_fact_mat_golden.py
-writes tests/golden/fact_mat_<case>.npz."""
+writes tests/golden/loader/fact_mat_<case>.npz."""
 import os
 import sys
 
@@ -26,6 +26,6 @@ if __name__ == "__main__":
         ld = FakeLoader(**kw)
         np.random.seed(seed)
         h, r, t, b, f, w, wr = fn(ld, ids, dropout)
-        np.savez(os.path.join(HERE, "fact_mat_%s.npz" % name), heads=h, rels=r, tails=t, batch_ids=b, fact_ids=f,
+        np.savez(os.path.join(HERE, "loader", "fact_mat_%s.npz" % name), heads=h, rels=r, tails=t, batch_ids=b, fact_ids=f,
                  weight_list=np.asarray(w, dtype=np.float64), weight_rel_list=np.asarray(wr, dtype=np.float64))
         print(name, len(h), "facts")

@@ -1,6 +1,6 @@
 """CPU: gnn_rag_b200.loader.build_fact_mat is a bit-identical drop-in for the reference's
 BasicDataLoader._build_fact_mat (gnn/dataset_load.py:473-527) -- against golden outputs of the unmodified reference
-(tests/golden/fact_mat_*.npz, made by tests/golden/make_fact_mat_golden.py) and, where the reference checkout is
+(tests/golden/loader/fact_mat_*.npz, made by tests/golden/make_fact_mat_golden.py) and, where the reference checkout is
 present, against the reference function itself on larger random loader states (with a timing comparison)."""
 import os
 import time
@@ -12,7 +12,7 @@ from gnn_rag_b200 import loader
 from loader_fixture import CASES, FakeLoader
 from oracle import ref_harness
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loader")
 KEYS = ("heads", "rels", "tails", "batch_ids", "fact_ids", "weight_list", "weight_rel_list")
 
 
