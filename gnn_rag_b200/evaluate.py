@@ -115,6 +115,38 @@ class Evaluator:
         return float(np.mean(f1s)), float(np.mean(hits)), float(np.mean(ems))
 
 
+def merge_candidates(cand1, cand2):
+    """Union of two GNNs' candidate lists as the LLM stage builds it (``load_gnn_rag``,
+    llm/src/qa_prediction/predict_answer.py:61-75): an entity present in both keeps the larger score in place,
+    new entities are appended in ``cand2`` order, then a STABLE sort by score, descending.  ``cand*`` are the
+    ``[[entity, prob], ...]`` lists of two ``.info`` rows; returns a new list (inputs untouched).  O(n) with a dict
+    instead of the reference's nested loop; same result including tie order."""
+    out = [[c[0], c[1]] for c in cand1]
+    pos = {}
+    for i, c in enumerate(out):
+        pos.setdefault(c[0], i)                   # the reference's inner loop stops at the FIRST match
+    for e, p in cand2:
+        i = pos.get(e)
+        if i is None:
+            pos[e] = len(out)
+            out.append([e, p])
+        elif p > out[i][1]:
+            out[i][1] = p
+    return sorted(out, key=lambda x: x[1], reverse=True)
+
+
+def merge_info_rows(rows1, rows2):
+    """Row-wise :func:`merge_candidates` of two ``.info`` row lists of the same questions (same order, as written by
+    :class:`Evaluator` for two models): returns copies of ``rows1`` with the merged ``cand``."""
+    assert len(rows1) == len(rows2)
+    out = []
+    for a, b in zip(rows1, rows2):
+        r = dict(a)
+        r["cand"] = merge_candidates(a["cand"], b["cand"])
+        out.append(r)
+    return out
+
+
 def path_node_sets(db, retrieved, max_targets=32):
     """Shortest-path node sets seed -> retrieved candidates on the undirected subgraph
     (llm/src/utils/graph_utils.py:10-21,49-75), computed on device (csrc/paths.cu).

@@ -122,3 +122,36 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def _reference_merge(cand1, cand2):
+    """The candidate-union loop of load_gnn_rag, llm/src/qa_prediction/predict_answer.py:61-75, restated."""
+    cand1 = [list(c) for c in cand1]
+    for c2 in cand2:
+        found = False
+        for c1 in cand1:
+            if c2[0] == c1[0]:
+                if c2[1] > c1[1]:
+                    c1[1] = c2[1]
+                found = True
+                break
+        if not found:
+            cand1.append(list(c2))
+    return sorted(cand1, key=lambda x: x[1], reverse=True)
+
+
+def test_merge_candidates_matches_the_llm_stage_union():
+    from gnn_rag_b200 import evaluate
+    rs = np.random.RandomState(0)
+    for _ in range(50):
+        ents = ["m.%d" % e for e in rs.randint(0, 12, 20)]
+        n1, n2 = rs.randint(0, 9), rs.randint(0, 9)
+        # scores on a coarse grid -> exact ties, duplicates inside a list -> first-match semantics
+        c1 = [[ents[i], float(rs.randint(0, 5)) / 4] for i in range(n1)]
+        c2 = [[ents[10 + i], float(rs.randint(0, 5)) / 4] for i in range(n2)]
+        keep1, keep2 = [list(c) for c in c1], [list(c) for c in c2]
+        assert evaluate.merge_candidates(c1, c2) == _reference_merge(c1, c2)
+        assert c1 == keep1 and c2 == keep2                        # inputs untouched
+    rows1 = [{"question": "q", "cand": [["a", 0.6], ["b", 0.3]]}]
+    rows2 = [{"question": "q", "cand": [["b", 0.5], ["c", 0.4]]}]
+    assert evaluate.merge_info_rows(rows1, rows2)[0]["cand"] == [["a", 0.6], ["b", 0.5], ["c", 0.4]]
