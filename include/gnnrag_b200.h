@@ -95,7 +95,8 @@ int gr_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const fl
 /* Tensor-core variant of gr_linear for the big e2e_linear GEMMs (reasongnn.py:163, nsm_gnn.py:63):
  * fp32 in / fp32 out with fp32-class accuracy through the 3-product split-bf16 scheme on tcgen05
  * (x = hi + lo in bf16; A W^T ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T, fp32 accumulation in TMEM,
- * dropped term <= 2^-18 relative).  TMA-fed, 128 x N x 64 tiles, one CTA per 128 rows.  Requires
+ * dropped term <= 2^-18 relative).  Persistent, TMA-fed 128 x N tiles over 32- or 64-column k-blocks ("tc_bk"),
+ * W shared across a CTA pair by TMA multicast ("tc_cluster"), TMA-store epilogue ("tc_tma_store").  Requires
  * 8 <= N <= 256.  The workspace (256-byte aligned, gr_linear_tc_workspace_bytes) holds the bf16 planes.
  * flags: GR_LINEAR_RELU. */
 size_t gr_linear_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
@@ -111,7 +112,8 @@ int gr_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const
  * Segmented K: when k_seg_pitch > k_seg > 0 the A planes hold K/k_seg_pitch segments of k_seg valid columns
  * at pitch k_seg_pitch (zero padding in between) while W is the dense [N, (K/k_seg_pitch)*k_seg] torch weight;
  * the W planes are built in the padded layout.  K is the padded length.
- * Workspace: gr_linear_tc_planes_workspace_bytes(N, K) (the W planes), 256-byte aligned. */
+ * Workspace: gr_linear_tc_planes_workspace_bytes(N, K) (the W planes), 256-byte aligned.
+ * flags: GR_LINEAR_RELU, GR_LINEAR_W_PRESPLIT (the workspace still holds this W's planes: skip the conversion). */
 size_t gr_linear_tc_planes_workspace_bytes(int64_t N, int64_t K);
 int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t lda16, const float* W, int64_t ldw,
                         const float* bias, float* C, int64_t ldc, void* C_hi, void* C_lo, int64_t ldc16,
