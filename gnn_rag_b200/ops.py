@@ -333,6 +333,9 @@ def _weight_ws(W, N, K, k_seg, k_seg_pitch, nbytes):
             return ent[0], False          # same buffer, re-split
     ws = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
     if WEIGHT_CACHE and not capturing:
+        if len(_W_CACHE) > 512:          # models that were dropped: release the workspaces of dead weights
+            for k in [k for k, e in _W_CACHE.items() if e[2]() is None]:
+                del _W_CACHE[k]
         _W_CACHE[key] = [ws, W._version, weakref.ref(_base(W))]
     return ws, False
 
