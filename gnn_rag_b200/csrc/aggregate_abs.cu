@@ -33,7 +33,9 @@
 
 namespace gr {
 
-int g_opt_agg_abs_ws = 1;     // gr_set_option("agg_abs_ws", 0|1): persistent warp-specialised kernel when a tile counter is given
+int g_opt_agg_abs_ws = 1;     // gr_set_option("agg_abs_ws", 0|1|2..): persistent warp-specialised kernel when a tile counter is given;
+                              // >= 2: TMA-gather variants (agg_abs_tma_kernel)
+int g_opt_agg_hot_rel = -1;   // gr_set_option("agg_hot_rel", id): relation row kept resident by the TMA-gather kernel
 
 namespace {
 
@@ -61,6 +63,7 @@ struct PnParams {
   int64_t ld, out_col0, Nt;
   int B, N, I, j0;
   int32_t* tile_counter;   // persistent kernel: dynamic tile scheduler (zeroed before the launch)
+  int hot_rel;             // TMA-gather kernel: relation whose table row stays resident in shared memory (-1: none)
 };
 
 __device__ __forceinline__ float4 ldg4(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -94,14 +97,16 @@ __device__ __forceinline__ void emit4(__nv_bfloat16* ph, __nv_bfloat16* pl, bool
   y01 = __ffma2_rn(make_float2(xn.x, xn.y), make_float2(V.x, V.y), y01);
   y23 = __ffma2_rn(make_float2(xn.z, xn.w), make_float2(V.z, V.w), y23);
   const __nv_bfloat162 h01 = __floats2bfloat162_rn(y01.x, y01.y), h23 = __floats2bfloat162_rn(y23.x, y23.y);
-  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  // bf16x2 -> float2 by hand: low half << 16, high half masked (2 ALU ops per pair; the library routine compiles to 4)
+  const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+  const float2 f01 = make_float2(__uint_as_float(u01 << 16), __uint_as_float(u01 & 0xffff0000u));
+  const float2 f23 = make_float2(__uint_as_float(u23 << 16), __uint_as_float(u23 & 0xffff0000u));
   const float2 m1 = make_float2(-1.f, -1.f);
   const float2 r01 = __ffma2_rn(f01, m1, y01), r23 = __ffma2_rn(f23, m1, y23);   // y - hi, exact, packed
   const __nv_bfloat162 l01 = __floats2bfloat162_rn(r01.x, r01.y);
   const __nv_bfloat162 l23 = __floats2bfloat162_rn(r23.x, r23.y);
   if (pred) {
-    *reinterpret_cast<uint2*>(ph) =
-        make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    *reinterpret_cast<uint2*>(ph) = make_uint2(u01, u23);
     *reinterpret_cast<uint2*>(pl) =
         make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   }
@@ -130,6 +135,7 @@ __device__ __forceinline__ void row_unit(const int2* __restrict__ rc, int beg, i
                                          const float* __restrict__ prior, const char* tb, const LaneIns<NI>& x,
                                          __nv_bfloat16* hrow, __nv_bfloat16* lrow, int seg_d, bool ld1, bool wr1) {
   float4 S0 = zero4(), S1 = S0, Q0 = S0, Q1 = S0;
+  float4 v01 = zero4(), v11 = zero4();                     // lanes without chunk-1 columns never overwrite these
   const int fast_end = min(end, kEdgeCap);
   int i = beg;
   for (; i + 1 < fast_end; i += 2) {                       // two edges per step: 4 x 16-byte loads in flight per lane
@@ -137,7 +143,7 @@ __device__ __forceinline__ void row_unit(const int2* __restrict__ rc, int beg, i
     const char* a0 = tb + (uint32_t)m0.x;
     const char* a1 = tb + (uint32_t)m1.x;
     const float4 v00 = ldg4(a0), v10 = ldg4(a1);
-    const float4 v01 = ld1 ? ldg4(a0 + 512) : zero4(), v11 = ld1 ? ldg4(a1 + 512) : zero4();
+    if (ld1) { v01 = ldg4(a0 + 512); v11 = ldg4(a1 + 512); }
     const float c0 = __int_as_float(m0.y), c1 = __int_as_float(m1.y);
     fma4(S0, c0, v00); fma4_abs(Q0, c0, v00); fma4(S1, c0, v01); fma4_abs(Q1, c0, v01);
     fma4(S0, c1, v10); fma4_abs(Q0, c1, v10); fma4(S1, c1, v11); fma4_abs(Q1, c1, v11);
@@ -146,7 +152,7 @@ __device__ __forceinline__ void row_unit(const int2* __restrict__ rc, int beg, i
     const int2 m0 = rc[i];
     const char* a0 = tb + (uint32_t)m0.x;
     const float4 v00 = ldg4(a0);
-    const float4 v01 = ld1 ? ldg4(a0 + 512) : zero4();
+    if (ld1) v01 = ldg4(a0 + 512);
     const float c0 = __int_as_float(m0.y);
     fma4(S0, c0, v00); fma4_abs(Q0, c0, v00); fma4(S1, c0, v01); fma4_abs(Q1, c0, v01);
   }
@@ -156,8 +162,8 @@ __device__ __forceinline__ void row_unit(const int2* __restrict__ rc, int beg, i
     const float c = w * (w * prior[dd.src[e]]);
     const char* a = tb + (uint32_t)dd.rel[e] * (uint32_t)kPnRowBytes;
     const float4 v0 = ldg4(a);
-    const float4 v1 = ld1 ? ldg4(a + 512) : zero4();
-    fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+    if (ld1) v01 = ldg4(a + 512);
+    fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v01); fma4_abs(Q1, c, v01);
   }
   const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);   // 2 * sum c*relu(v), 2 * sum c*relu(-v)
   const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
@@ -294,15 +300,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive1(uint64_t* b) { mbar_arrive(b); }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity)
+        : "r"(smem_u32(b)), "r"(parity), "r"(20000u)     // suspend-time hint [ns]: an idle role polls rarely
         : "memory");
   }
 }
@@ -315,6 +322,60 @@ struct alignas(16) WsBuf {
   int32_t tile;
 };
 static_assert(sizeof(WsBuf<2>) % 16 == 0, "double buffer halves must stay 16-byte aligned");
+
+
+// Producer side of the persistent kernels: stage one 64-row tile (row pointers, relu(+-ins)/2 of its <= 2 questions,
+// {table byte offset, coefficient} per edge of both directions) into `bf`.  One warp.
+template <int NI, int DT, int CAP, bool FLAG_HOT, class Buf>
+__device__ __forceinline__ void produce_tile(Buf& bf, const PnParams& p, int tile, int lane) {
+  const int N = p.N;
+  const int64_t r0 = (int64_t)tile * kRows;
+  const int nrows = (int)min((int64_t)kRows, p.Nt - r0);
+  const int b0 = (int)(r0 / N);
+  if (lane == 0) bf.tile = tile;
+  int eb[2], ne[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int32_t* rp = p.dir[d].rowptr + r0;
+    const int e0 = __ldg(rp), e1 = __ldg(rp + nrows);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = lane + 32 * k;
+      if (i <= nrows) bf.rowptr[d][i] = __ldg(rp + i);
+    }
+    eb[d] = e0;
+    ne[d] = min(e1 - e0, CAP);
+  }
+  stage_ins<NI, DT>(bf.x, p, b0, lane, 32);
+  // edge slice -> {table byte offset, coefficient}; 4 edges per lane in flight
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const PnDir& dd = p.dir[d];
+    for (int i0 = 0; i0 < ne[d]; i0 += 128) {
+      int sidx[4], ridx[4];
+      float wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + 32 * u;
+        const bool ok = i < ne[d];
+        sidx[u] = ok ? __ldg(dd.src + eb[d] + i) : 0;
+        ridx[u] = ok ? __ldg(dd.rel + eb[d] + i) : 0;
+        wv[u] = (ok && dd.w) ? __ldg(dd.w + eb[d] + i) : 1.0f;
+      }
+      float pr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pr[u] = __ldg(p.prior + sidx[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + 32 * u;
+        if (i < ne[d])
+          bf.rc[d][i] = make_int2((int)((uint32_t)ridx[u] * (uint32_t)kPnRowBytes) |
+                                      ((FLAG_HOT && ridx[u] == p.hot_rel) ? 1 : 0),
+                                  __float_as_int(wv[u] * (wv[u] * pr[u])));
+      }
+    }
+  }
+}
 
 template <int NI, int DT, int SEGP>
 __global__ void __launch_bounds__(kWsThreads, 2) agg_abs_ws_kernel(const PnParams p, int ntiles) {
@@ -344,51 +405,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) agg_abs_ws_kernel(const PnParam
         mbar_arrive(&s_full[it & 1]);
         break;
       }
-      const int64_t r0 = (int64_t)tile * kRows;
-      const int nrows = (int)min((int64_t)kRows, p.Nt - r0);
-      const int b0 = (int)(r0 / N);
-      if (lane == 0) bf.tile = tile;
-      int eb[2], ne[2];
-#pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        const int32_t* rp = p.dir[d].rowptr + r0;
-        const int e0 = __ldg(rp), e1 = __ldg(rp + nrows);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int i = lane + 32 * k;
-          if (i <= nrows) bf.rowptr[d][i] = __ldg(rp + i);
-        }
-        eb[d] = e0;
-        ne[d] = min(e1 - e0, kEdgeCap);
-      }
-      stage_ins<NI, DT>(bf.x, p, b0, lane, 32);
-      // edge slice -> {table byte offset, coefficient}; 4 edges per lane in flight
-#pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        const PnDir& dd = p.dir[d];
-        for (int i0 = 0; i0 < ne[d]; i0 += 128) {
-          int sidx[4], ridx[4];
-          float wv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + lane + 32 * u;
-            const bool ok = i < ne[d];
-            sidx[u] = ok ? __ldg(dd.src + eb[d] + i) : 0;
-            ridx[u] = ok ? __ldg(dd.rel + eb[d] + i) : 0;
-            wv[u] = (ok && dd.w) ? __ldg(dd.w + eb[d] + i) : 1.0f;
-          }
-          float pr[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) pr[u] = __ldg(p.prior + sidx[u]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + lane + 32 * u;
-            if (i < ne[d])
-              bf.rc[d][i] = make_int2((int)((uint32_t)ridx[u] * (uint32_t)kPnRowBytes),
-                                      __float_as_int(wv[u] * (wv[u] * pr[u])));
-          }
-        }
-      }
+      produce_tile<NI, DT, kEdgeCap, false>(bf, p, tile, lane);
       __syncwarp();
       mbar_arrive(&s_full[it & 1]);
     }
@@ -433,6 +450,999 @@ __global__ void __launch_bounds__(kWsThreads, 2) agg_abs_ws_kernel(const PnParam
   }
 }
 
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Software-pipelined consumers (gr_set_option("agg_abs_ws", 6)): same producer / buffers as agg_abs_ws_kernel, but a
+// consumer warp issues the gather loads of the first two edges of its NEXT (row, direction) unit before it runs the
+// epilogue of the current one (bf16 hi/lo split + stores, ~75 instructions without a memory dependence), so that
+// L2 latency is covered by the epilogue instead of by other warps (there are only 4 per scheduler).  Missing edges
+// of a short unit are replaced by (table row 0, coefficient 0): fma(0, finite, acc) == acc, branch-free.
+// ---------------------------------------------------------------------------------------------------------
+struct Pre2 {
+  float4 v00, v01, v10, v11;
+  float c0, c1;
+};
+
+template <int NI, int DT, int SEGP>
+__global__ void __launch_bounds__(kWsThreads, 2) agg_abs_ws2_kernel(const PnParams p, int ntiles) {
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  WsBuf<NI>* bufs = reinterpret_cast<WsBuf<NI>*>(ws_smem);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], kThreads); mbar_init(&s_empty[1], kThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kWarps) {
+    for (int it = 0;; ++it) {
+      WsBuf<NI>& bf = bufs[it & 1];
+      if (it >= 2) mbar_wait(&s_empty[it & 1], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[it & 1]);
+        break;
+      }
+      produce_tile<NI, DT, kEdgeCap, false>(bf, p, tile, lane);
+      __syncwarp();
+      mbar_arrive(&s_full[it & 1]);
+    }
+    return;
+  }
+
+  const bool ld1 = 128 + lane * 4 < DT;
+  const bool wr1 = 128 + lane * 4 < SEGP;
+  const char* const tb0 = reinterpret_cast<const char*>(p.dir[0].pn) + lane * 16;
+  const char* const tb1 = reinterpret_cast<const char*>(p.dir[1].pn) + lane * 16;
+  LaneIns<NI> x;
+  Pre2 pre;
+  pre.v01 = zero4(); pre.v11 = zero4();
+  for (int it = 0;; ++it) {
+    WsBuf<NI>& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int64_t r0 = (int64_t)tile * kRows;
+    const int nrows = (int)min((int64_t)kRows, p.Nt - r0);
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    __nv_bfloat16* const hi_lane = p.out_hi + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* const lo_lane = p.out_lo + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    const int nunits = warp < nrows ? 2 * ((nrows - warp + kWarps - 1) / kWarps) : 0;
+    const int eb0 = bf.rowptr[0][0], eb1 = bf.rowptr[1][0];
+
+    // issue the gather of the first two staged edges of unit u into `pre`
+    auto prefetch = [&](int u) {
+      const int d = u & 1, lr = warp + kWarps * (u >> 1);
+      const int ebase = d ? eb1 : eb0;
+      const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+      const int nf = min(end, kEdgeCap) - beg;                 // staged edges of the unit (may be <= 0)
+      const int2 m0 = nf >= 1 ? bf.rc[d][beg] : make_int2(0, 0);
+      const int2 m1 = nf >= 2 ? bf.rc[d][beg + 1] : make_int2(0, 0);
+      const char* tb = d ? tb1 : tb0;
+      const char* a0 = tb + (uint32_t)m0.x;
+      const char* a1 = tb + (uint32_t)m1.x;
+      pre.v00 = ldg4(a0); pre.v10 = ldg4(a1);
+      if (ld1) { pre.v01 = ldg4(a0 + 512); pre.v11 = ldg4(a1 + 512); }
+      pre.c0 = __int_as_float(m0.y); pre.c1 = __int_as_float(m1.y);
+    };
+
+    int cur_q = -1;
+    if (nunits > 0) prefetch(0);
+    for (int u = 0; u < nunits; ++u) {
+      const int d = u & 1, lr = warp + kWarps * (u >> 1);
+      const int q = lr >= lr_switch ? 1 : 0;
+      if (q != cur_q) {
+        cur_q = q;
+        x.load(&bf.x[q][0][0][lane * 4]);
+      }
+      const int ebase = d ? eb1 : eb0;
+      const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+      const int fast_end = min(end, kEdgeCap);
+      const int2* __restrict__ rc = bf.rc[d];
+      const char* tb = d ? tb1 : tb0;
+      float4 S0 = zero4(), S1 = S0, Q0 = S0, Q1 = S0;
+      // the two prefetched edges (coefficient 0 where the unit is shorter)
+      fma4(S0, pre.c0, pre.v00); fma4_abs(Q0, pre.c0, pre.v00); fma4(S1, pre.c0, pre.v01); fma4_abs(Q1, pre.c0, pre.v01);
+      fma4(S0, pre.c1, pre.v10); fma4_abs(Q0, pre.c1, pre.v10); fma4(S1, pre.c1, pre.v11); fma4_abs(Q1, pre.c1, pre.v11);
+      {
+        float4 v01 = zero4(), v11 = zero4();
+        int i = beg + 2;
+        for (; i + 1 < fast_end; i += 2) {
+          const int2 m0 = rc[i], m1 = rc[i + 1];
+          const char* a0 = tb + (uint32_t)m0.x;
+          const char* a1 = tb + (uint32_t)m1.x;
+          const float4 v00 = ldg4(a0), v10 = ldg4(a1);
+          if (ld1) { v01 = ldg4(a0 + 512); v11 = ldg4(a1 + 512); }
+          const float c0 = __int_as_float(m0.y), c1 = __int_as_float(m1.y);
+          fma4(S0, c0, v00); fma4_abs(Q0, c0, v00); fma4(S1, c0, v01); fma4_abs(Q1, c0, v01);
+          fma4(S0, c1, v10); fma4_abs(Q0, c1, v10); fma4(S1, c1, v11); fma4_abs(Q1, c1, v11);
+        }
+        if (i < fast_end) {
+          const int2 m0 = rc[i];
+          const char* a0 = tb + (uint32_t)m0.x;
+          const float4 v00 = ldg4(a0);
+          if (ld1) v01 = ldg4(a0 + 512);
+          const float c0 = __int_as_float(m0.y);
+          fma4(S0, c0, v00); fma4_abs(Q0, c0, v00); fma4(S1, c0, v01); fma4_abs(Q1, c0, v01);
+        }
+        const PnDir& dd = p.dir[d];
+        for (i = max(beg, kEdgeCap); i < end; ++i) {           // slow path: slice overflowed the staging buffer
+          const int64_t e = (int64_t)ebase + i;
+          const float w = dd.w ? dd.w[e] : 1.0f;
+          const float c = w * (w * p.prior[dd.src[e]]);
+          const char* a = tb + (uint32_t)dd.rel[e] * (uint32_t)kPnRowBytes;
+          const float4 v0 = ldg4(a);
+          if (ld1) v01 = ldg4(a + 512);
+          fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v01); fma4_abs(Q1, c, v01);
+        }
+      }
+      if (u + 1 < nunits) prefetch(u + 1);                     // loads fly while the epilogue below runs
+      __nv_bfloat16* const hrow = hi_lane + (int64_t)lr * p.ld;
+      __nv_bfloat16* const lrow = lo_lane + (int64_t)lr * p.ld;
+      const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);
+      const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int seg = d * SEGP + j * 2 * SEGP;
+        emit4(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
+        emit4(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
+      }
+    }
+    mbar_arrive(&s_empty[it & 1]);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Half-row consumers (gr_set_option("agg_abs_ws", 7)).
+//
+// ncu on agg_abs_ws_kernel (profiles/r2_*): 246 warp instructions per (row, direction) unit at 48 % issue-slot
+// utilisation; a consumer warp spends ~2300 cycles per unit, most of it in two dependent L2 round trips (two edges
+// per trip) -- the kernel is bound by the gather LATENCY per warp, and at 96 registers (32 of them the per-question
+// relu(+-ins) values of 8 columns per lane) only 16 consumer warps fit on an SM.  Here a destination row is shared
+// by a PAIR of warps, each owning one column half (columns [0,96) / [96,208): the boundary is a whole 32-byte
+// sector in both the table row and the bf16 planes) with 4 columns per lane: half the live state per thread ->
+// 64 registers -> 28 consumer warps per SM, and every warp keeps 4 edges in flight (one round trip for a row of <= 4
+// in-edges).  Bytes of gather in flight per SM: 28 x 4 x ~400 B = 45 KB instead of 16 x 2 x 800 B = 26 KB.
+// Same producer, same staged {offset, coefficient} slices, same summation order (slot order within the row) ->
+// bit-identical results.  Tiles are 56 rows (7 warp pairs x 8 rows).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kHalfSplit = 96;     // first column of the second half (multiple of 16 bf16 / 8 fp32: sector aligned)
+
+template <int NI, int ROWS>
+struct alignas(16) HBuf {
+  int2 rc[2][kEdgeCap];
+  float x[2][NI][2][kPnCols];
+  int32_t rowptr[2][ROWS + 4];
+  int32_t tile;
+  int32_t pad_[3];
+};
+
+template <int NI, int DT, int ROWS, int CAP = kEdgeCap, class Buf>
+__device__ __forceinline__ void produce_tile_rows(Buf& bf, const PnParams& p, int tile, int lane) {
+  // The producer is ONE warp running dependent global loads (row pointers -> src / rel slices -> prior[src]); what
+  // bounds it is the number of round trips per tile, not the instruction count.  Both directions and up to 8 edges
+  // per lane and direction are therefore fetched per batch (a 64-row cfg2 tile has ~256 edges per direction: one
+  // batch): 3 round trips per tile.  (The first version took 128 edges of one direction per batch: ~10 trips, and
+  // the consumers of a tile were waiting for it: profiles/README.md.)
+  constexpr int U = 8;
+  const int N = p.N;
+  const int64_t r0 = (int64_t)tile * ROWS;
+  const int nrows = (int)min((int64_t)ROWS, p.Nt - r0);
+  const int b0 = (int)(r0 / N);
+  if (lane == 0) bf.tile = tile;
+  int eb[2], ne[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int32_t* rp = p.dir[d].rowptr + r0;
+    eb[d] = __ldg(rp);
+    ne[d] = __ldg(rp + nrows);
+  }
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int32_t* rp = p.dir[d].rowptr + r0;
+#pragma unroll
+    for (int k = 0; k < (ROWS + 32) / 32; ++k) {
+      const int i = lane + 32 * k;
+      if (i <= nrows) bf.rowptr[d][i] = __ldg(rp + i);
+    }
+    ne[d] = min(ne[d] - eb[d], CAP);
+  }
+  const int nmax = max(ne[0], ne[1]);
+  const bool has_w = p.dir[0].w != nullptr || p.dir[1].w != nullptr;
+  for (int i0 = 0; i0 < nmax; i0 += 32 * U) {
+    int sidx[2][U], ridx[2][U];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const PnDir& dd = p.dir[d];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + lane + 32 * u;
+        const bool ok = i < ne[d];
+        sidx[d][u] = ok ? __ldg(dd.src + eb[d] + i) : 0;
+        ridx[d][u] = ok ? __ldg(dd.rel + eb[d] + i) : 0;
+      }
+    }
+    if (i0 == 0) stage_ins<NI, DT>(bf.x, p, b0, lane, 32);   // overlaps the first batch's index loads
+    float pr[2][U];
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int u = 0; u < U; ++u) pr[d][u] = __ldg(p.prior + sidx[d][u]);
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const PnDir& dd = p.dir[d];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + lane + 32 * u;
+        if (i < ne[d]) {
+          const float w = (has_w && dd.w) ? __ldg(dd.w + eb[d] + i) : 1.0f;
+          bf.rc[d][i] = make_int2((int)((uint32_t)ridx[d][u] * (uint32_t)kPnRowBytes),
+                                  __float_as_int(w * (w * pr[d][u])));
+        }
+      }
+    }
+  }
+  if (nmax <= 0) stage_ins<NI, DT>(bf.x, p, b0, lane, 32);
+}
+
+// y = xp*U + xn*V -> bf16 hi/lo, one 8-byte store per plane
+__device__ __forceinline__ void emit4h(__nv_bfloat16* ph, __nv_bfloat16* pl, bool pred, const float4& xp,
+                                       const float4& xn, const float4& U, const float4& V) {
+  emit4(ph, pl, pred, xp, xn, U, V);
+}
+
+template <int NI, int DT, int SEGP, int SLOTS, int RPS>
+__global__ void __launch_bounds__((2 * SLOTS + 1) * 32, 2) agg_abs_half_kernel(const PnParams p, int ntiles) {
+  constexpr int ROWS = SLOTS * RPS;
+  constexpr int CW = 2 * SLOTS;                    // consumer warps
+  static_assert(DT % 4 == 0 && DT > kHalfSplit && DT <= kHalfSplit + 128 && SEGP <= kHalfSplit + 128, "two halves");
+  using Buf = HBuf<NI, ROWS>;
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  Buf* bufs = reinterpret_cast<Buf*>(ws_smem);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], CW * 32); mbar_init(&s_empty[1], CW * 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == CW) {
+    // =============================== producer warp ===============================
+    for (int it = 0;; ++it) {
+      Buf& bf = bufs[it & 1];
+      if (it >= 2) mbar_wait(&s_empty[it & 1], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[it & 1]);
+        break;
+      }
+      produce_tile_rows<NI, DT, ROWS>(bf, p, tile, lane);
+      __syncwarp();
+      mbar_arrive(&s_full[it & 1]);
+    }
+    return;
+  }
+
+  // =============================== consumer warps: (slot, column half) ===============================
+  const int slot = warp >> 1, half = warp & 1;
+  const int col0 = half * kHalfSplit + lane * 4;                      // first of this lane's 4 columns
+  const bool ld = col0 < DT && (half == 1 || lane * 4 < kHalfSplit);   // lane owns real table columns
+  const bool wr = col0 < SEGP && (half == 1 || lane * 4 < kHalfSplit); // lane owns segment columns (incl. zero pad)
+  const char* const tb0 = reinterpret_cast<const char*>(p.dir[0].pn) + col0 * 4;
+  const char* const tb1 = reinterpret_cast<const char*>(p.dir[1].pn) + col0 * 4;
+  float4 xp[NI], xn[NI];
+  for (int it = 0;; ++it) {
+    Buf& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int64_t r0 = (int64_t)tile * ROWS;
+    const int nrows = (int)min((int64_t)ROWS, p.Nt - r0);
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    __nv_bfloat16* const hi_lane = p.out_hi + r0 * p.ld + p.out_col0 + col0 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* const lo_lane = p.out_lo + r0 * p.ld + p.out_col0 + col0 + (int64_t)p.j0 * 2 * SEGP;
+    int cur_q = -1;
+    for (int lr = slot; lr < nrows; lr += SLOTS) {
+      const int q = lr >= lr_switch ? 1 : 0;
+      if (q != cur_q) {
+        cur_q = q;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          xp[j] = wr ? *reinterpret_cast<const float4*>(&bf.x[q][j][0][col0 & (kPnCols - 1)]) : zero4();
+          xn[j] = wr ? *reinterpret_cast<const float4*>(&bf.x[q][j][1][col0 & (kPnCols - 1)]) : zero4();
+        }
+      }
+      __nv_bfloat16* const hrow = hi_lane + (int64_t)lr * p.ld;
+      __nv_bfloat16* const lrow = lo_lane + (int64_t)lr * p.ld;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int ebase = bf.rowptr[d][0];
+        const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+        const int fast_end = min(end, kEdgeCap);
+        const int2* __restrict__ rc = bf.rc[d];
+        const char* tb = d ? tb1 : tb0;
+        float4 S = zero4(), Q = zero4();
+        float4 v0 = zero4(), v1 = zero4(), v2 = zero4(), v3 = zero4();   // lanes without table columns keep zeros
+        for (int i = beg; i < fast_end; i += 4) {
+          const int n = fast_end - i;
+          const int2 m0 = rc[i];
+          const int2 m1 = rc[n > 1 ? i + 1 : i];
+          if (n > 2) {                                       // 3 or 4 edges: four loads in flight
+            const int2 m2 = rc[i + 2];
+            const int2 m3 = rc[n > 3 ? i + 3 : i + 2];
+            if (ld) {
+              v0 = ldg4(tb + (uint32_t)m0.x); v1 = ldg4(tb + (uint32_t)m1.x);
+              v2 = ldg4(tb + (uint32_t)m2.x); v3 = ldg4(tb + (uint32_t)m3.x);
+            }
+            const float c0 = __int_as_float(m0.y), c1 = __int_as_float(m1.y), c2 = __int_as_float(m2.y);
+            const float c3 = n > 3 ? __int_as_float(m3.y) : 0.f;
+            fma4(S, c0, v0); fma4_abs(Q, c0, v0);
+            fma4(S, c1, v1); fma4_abs(Q, c1, v1);
+            fma4(S, c2, v2); fma4_abs(Q, c2, v2);
+            fma4(S, c3, v3); fma4_abs(Q, c3, v3);
+          } else {
+            if (ld) { v0 = ldg4(tb + (uint32_t)m0.x); v1 = ldg4(tb + (uint32_t)m1.x); }
+            const float c0 = __int_as_float(m0.y);
+            const float c1 = n > 1 ? __int_as_float(m1.y) : 0.f;
+            fma4(S, c0, v0); fma4_abs(Q, c0, v0);
+            fma4(S, c1, v1); fma4_abs(Q, c1, v1);
+          }
+        }
+        {
+          const PnDir& dd = p.dir[d];
+          for (int i = max(beg, kEdgeCap); i < end; ++i) {   // slow path: slice overflowed the staging buffer
+            const int64_t e = (int64_t)ebase + i;
+            const float w = dd.w ? dd.w[e] : 1.0f;
+            const float c = w * (w * p.prior[dd.src[e]]);
+            if (ld) v0 = ldg4(tb + (uint32_t)dd.rel[e] * (uint32_t)kPnRowBytes);
+            fma4(S, c, v0); fma4_abs(Q, c, v0);
+          }
+        }
+        const float4 U = addsub4(Q, S, 1.f), V = addsub4(Q, S, -1.f);
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int seg = d * SEGP + j * 2 * SEGP;
+          emit4h(hrow + seg, lrow + seg, wr, xp[j], xn[j], U, V);
+        }
+      }
+    }
+    mbar_arrive(&s_empty[it & 1]);     // every consumer thread arrives
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Shape-generic persistent kernel (gr_set_option("agg_abs_ws", 10..)): the agg_abs_ws_kernel structure with the
+// number of consumer warps, the rows per tile and the resident CTAs per SM as template parameters.  The register
+// file is split per scheduler (16 K registers each): with W warps per CTA and MINB CTAs per SM the busiest scheduler
+// holds ceil(W * MINB / 4) warps, so 9-warp CTAs x 2 leave 96 registers per thread, 10-warp CTAs x 2 still 96 (5 warps
+// per scheduler on all four), 12-warp CTAs x 2 leave 80.
+// ---------------------------------------------------------------------------------------------------------
+template <int NI, int DT, int SEGP, int KW, int ROWS, int MINB>
+__global__ void __launch_bounds__((KW + 1) * 32, MINB) agg_abs_wsg_kernel(const PnParams p, int ntiles) {
+  using Buf = HBuf<NI, ROWS>;
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  Buf* bufs = reinterpret_cast<Buf*>(ws_smem);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], KW * 32); mbar_init(&s_empty[1], KW * 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == KW) {
+    for (int it = 0;; ++it) {
+      Buf& bf = bufs[it & 1];
+      if (it >= 2) mbar_wait(&s_empty[it & 1], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[it & 1]);
+        break;
+      }
+      produce_tile_rows<NI, DT, ROWS>(bf, p, tile, lane);
+      __syncwarp();
+      mbar_arrive(&s_full[it & 1]);
+    }
+    return;
+  }
+  const bool ld1 = 128 + lane * 4 < DT;
+  const bool wr1 = 128 + lane * 4 < SEGP;
+  const char* tb[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) tb[d] = reinterpret_cast<const char*>(p.dir[d].pn) + lane * 16;
+  LaneIns<NI> x;
+  for (int it = 0;; ++it) {
+    Buf& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int64_t r0 = (int64_t)tile * ROWS;
+    const int nrows = (int)min((int64_t)ROWS, p.Nt - r0);
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    __nv_bfloat16* const hi_lane = p.out_hi + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* const lo_lane = p.out_lo + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    int cur_q = -1;
+    for (int lr = warp; lr < nrows; lr += KW) {
+      const int q = lr >= lr_switch ? 1 : 0;
+      if (q != cur_q) {
+        cur_q = q;
+        x.load(&bf.x[q][0][0][lane * 4]);
+      }
+      __nv_bfloat16* const hrow = hi_lane + (int64_t)lr * p.ld;
+      __nv_bfloat16* const lrow = lo_lane + (int64_t)lr * p.ld;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int ebase = bf.rowptr[d][0];
+        const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+        row_unit<NI, DT, SEGP>(bf.rc[d], beg, end, ebase, p.dir[d], p.prior, tb[d], x, hrow, lrow, d * SEGP, ld1, wr1);
+      }
+    }
+    mbar_arrive(&s_empty[it & 1]);
+  }
+}
+
+template <int NI, int KW, int ROWS, int MINB>
+int launch_wsg(const PnParams& p, cudaStream_t stream) {
+  auto kern = agg_abs_wsg_kernel<NI, 200, 208, KW, ROWS, MINB>;
+  const size_t smem = 2 * sizeof(HBuf<NI, ROWS>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+  const unsigned tiles = (unsigned)ceil_div(p.Nt, ROWS);
+  const unsigned pgrid = std::min<unsigned>(tiles, (unsigned)MINB * (unsigned)sm_count());
+  kern<<<pgrid, (KW + 1) * 32, smem, stream>>>(p, (int)tiles);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-gather version of the persistent kernel (gr_set_option("agg_abs_ws", 2..4)).
+//
+// ncu on agg_abs_ws_kernel (profiles/r1b_agg_kernel.txt): DRAM 38 % and L2 41 % of peak, issue slots 48 % busy,
+// 58 % of the stall samples on long_scoreboard -- the per-lane LDGs of the gathered table rows: with 16 consumer
+// warps per SM and two edges in flight per warp there are ~25 KB of gather outstanding per SM, not enough to cover
+// the L2 latency.  Here the gather does not occupy warps at all: every consumer warp owns a private ring of NS
+// 800-byte slots in shared memory and issues one 1-D bulk copy (cp.async.bulk, SASS UBLKCP) per gathered edge --
+// lane i copies the table row of edge i of a (row, direction) unit -- for units up to kBars ahead of the one it is
+// accumulating; the unit's mbarrier (expect_tx = n * 800 bytes) flips when all its rows have landed, and the
+// accumulation loop reads the rows with conflict-free LDS.128.  Bytes in flight per SM = ring bytes (~150 KB)
+// instead of 25 KB.  The prefetch cursor runs across tile boundaries (it peeks at the producer's next tile with a
+// non-blocking mbarrier.test_wait), so there is no gather bubble at the start of a tile.
+//
+// Optional resident row (p.hot_rel >= 0): every real node carries a self-loop fact with the same relation id
+// (gnn/dataset_load.py:499-506), i.e. ~25 % of all gathered rows are ONE table row per direction.  The producer
+// flags those edges (bit 0 of the staged table offset); they are served from a copy of that row held in shared
+// memory for the whole launch and never enter the ring.  Pure optimisation: any hot_rel gives the same result.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTmaCap = 512;       // staged edges per direction per tile (mean 256 at cfg2); the rest -> slow path
+constexpr int kRingMaxUnit = 8;    // ring slots one (row, direction) unit may take; further staged edges use LDG
+constexpr int kBars = 4;           // units in flight per consumer warp
+
+template <int NI>
+struct alignas(16) TmaBuf {
+  int2 rc[2][kTmaCap];
+  float x[2][NI][2][kPnCols];
+  int32_t rowptr[2][kRows + 4];
+  int32_t tile;
+  int32_t pad_[3];
+};
+static_assert(sizeof(TmaBuf<2>) % 16 == 0, "double buffer halves must stay 16-byte aligned");
+
+__device__ __forceinline__ bool mbar_test(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NI, int DT, int SEGP, int KW, int NS, int MINB, bool HOT>
+__global__ void __launch_bounds__((KW + 1) * 32, MINB) agg_abs_tma_kernel(const PnParams p, int ntiles) {
+  static_assert(DT % 4 == 0 && DT > 128 && DT <= kPnCols && NS >= kRingMaxUnit, "two column chunks of 128");
+  using Buf = TmaBuf<NI>;
+  constexpr int kSlot = DT * 4;                    // bytes per gathered table row
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  Buf* bufs = reinterpret_cast<Buf*>(ws_smem);
+  unsigned char* ring_all = ws_smem + 2 * sizeof(Buf);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  __shared__ __align__(8) uint64_t s_bar[KW][kBars];
+  __shared__ __align__(16) float s_hot[2][kPnCols];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], KW * 32); mbar_init(&s_empty[1], KW * 32);
+    for (int w = 0; w < KW; ++w)
+      for (int b = 0; b < kBars; ++b) mbar_init(&s_bar[w][b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (HOT) {
+    for (int i = tid; i < 2 * kPnCols; i += (KW + 1) * 32) {
+      const int d = i / kPnCols, c = i % kPnCols;
+      s_hot[d][c] = p.hot_rel >= 0 ? __ldg(p.dir[d].pn + (int64_t)p.hot_rel * kPnCols + c) : 0.f;
+    }
+  }
+  __syncthreads();
+
+  if (warp == KW) {
+    // =============================== producer warp ===============================
+    for (int it = 0;; ++it) {
+      Buf& bf = bufs[it & 1];
+      if (it >= 2) mbar_wait(&s_empty[it & 1], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[it & 1]);
+        break;
+      }
+      produce_tile<NI, DT, kTmaCap, HOT>(bf, p, tile, lane);
+      __syncwarp();
+      mbar_arrive(&s_full[it & 1]);
+    }
+    return;
+  }
+
+  // =============================== consumer warps ===============================
+  const bool ld1 = 128 + lane * 4 < DT;
+  const bool wr1 = 128 + lane * 4 < SEGP;
+  const char* const pnb0 = reinterpret_cast<const char*>(p.dir[0].pn);
+  const char* const pnb1 = reinterpret_cast<const char*>(p.dir[1].pn);
+  unsigned char* const ring = ring_all + (size_t)warp * NS * kSlot;
+  const uint32_t ring_s = smem_u32(ring);
+  uint64_t* const bars = s_bar[warp];
+
+  // number of (row, direction) units this warp owns in the tile staged in `bf` (-1: end marker)
+  auto tile_units = [&](const Buf& bf) -> int {
+    const int t = bf.tile;
+    if (t < 0) return -1;
+    const int nr = (int)min((int64_t)kRows, p.Nt - (int64_t)t * kRows);
+    return warp < nr ? 2 * ((nr - warp + KW - 1) / KW) : 0;
+  };
+  // ring edges of unit u of the tile in `bf`: the first <= kRingMaxUnit non-resident edges among its first 32 staged
+  // edges.  Returns n; `mine` = this lane's edge is one of them, `rank` its slot rank, `off` its table offset.
+  auto unit_ring = [&](const Buf& bf, int u, bool& mine, int& rank, int& off, int& dd) -> int {
+    const int d = u & 1, lr = warp + KW * (u >> 1);
+    const int ebase = bf.rowptr[d][0];
+    const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+    const int cand = max(0, min(min(end, kTmaCap) - beg, 32));
+    dd = d;
+    if (!HOT) {
+      const int n = min(cand, kRingMaxUnit);
+      mine = lane < n;
+      rank = lane;
+      off = mine ? bf.rc[d][beg + lane].x : 0;
+      return n;
+    }
+    off = lane < cand ? bf.rc[d][beg + lane].x : 1;
+    const unsigned m = __ballot_sync(0xffffffffu, (off & 1) == 0);
+    rank = __popc(m & ((1u << lane) - 1u));
+    mine = (off & 1) == 0 && rank < kRingMaxUnit;
+    return min(__popc(m), kRingMaxUnit);
+  };
+
+  int p_it = 0, p_u = 0, p_nu = -2;     // prefetch cursor: tile iteration, unit, units in that tile (-2: not entered)
+  uint32_t seq_p = 0, seq_c = 0;        // units (with n > 0) issued / consumed
+  int head_p = 0, head_c = 0, used = 0; // ring slot cursors, slots in flight
+  LaneIns<NI> x;
+
+  for (int it = 0;; ++it) {
+    Buf& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int nunits = tile_units(bf);
+    if (p_it < it || p_nu == -2) { p_it = it; p_u = 0; p_nu = nunits; }
+    const int64_t r0 = (int64_t)tile * kRows;
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    __nv_bfloat16* const hi_lane = p.out_hi + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* const lo_lane = p.out_lo + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    int cur_q = -1;
+    for (int u = 0; u < nunits; ++u) {
+      // ---------------- prefetch: issue the bulk copies of units ahead of u ----------------
+      for (;;) {
+        if (p_u >= p_nu) {                               // cursor at the end of its tile: try to enter the next one
+          if (p_nu < 0 || p_it > it) break;              // end marker seen / already one tile ahead
+          if (!mbar_test(&s_full[(p_it + 1) & 1], ((p_it + 1) >> 1) & 1)) break;
+          ++p_it; p_u = 0;
+          p_nu = tile_units(bufs[p_it & 1]);
+          continue;
+        }
+        if (seq_p - seq_c >= (uint32_t)kBars) break;
+        bool mine; int rank, off, d;
+        const int n = unit_ring(bufs[p_it & 1], p_u, mine, rank, off, d);
+        if (used + n > NS) break;
+        if (n > 0) {
+          uint64_t* bar = &bars[seq_p % kBars];
+          if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n * kSlot));
+          __syncwarp();
+          if (mine) {
+            int slot = head_p + rank;
+            slot = slot >= NS ? slot - NS : slot;
+            bulk_g2s(ring_s + (uint32_t)(slot * kSlot), (d ? pnb1 : pnb0) + (uint32_t)off, (uint32_t)kSlot, bar);
+          }
+          head_p += n; head_p = head_p >= NS ? head_p - NS : head_p;
+          used += n;
+          ++seq_p;
+        }
+        ++p_u;
+      }
+      // ---------------- consume unit u ----------------
+      const int d = u & 1, lr = warp + KW * (u >> 1);
+      const int q = lr >= lr_switch ? 1 : 0;
+      if (q != cur_q) {
+        cur_q = q;
+        x.load(&bf.x[q][0][0][lane * 4]);
+      }
+      __nv_bfloat16* const hrow = hi_lane + (int64_t)lr * p.ld;
+      __nv_bfloat16* const lrow = lo_lane + (int64_t)lr * p.ld;
+      const int ebase = bf.rowptr[d][0];
+      const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+      const int fast_end = min(end, kTmaCap);
+      int n;
+      {
+        bool mine; int rank, off, dd;
+        n = unit_ring(bf, u, mine, rank, off, dd);
+      }
+      if (n > 0) {
+        mbar_wait(&bars[seq_c % kBars], (seq_c / kBars) & 1);
+        ++seq_c;
+      }
+      const int2* __restrict__ rc = bf.rc[d];
+      float4 S0 = zero4(), S1 = S0, Q0 = S0, Q1 = S0;
+      int slot = head_c, taken = 0;
+      for (int i = beg; i < fast_end; ++i) {
+        const int2 m = rc[i];
+        const float c = __int_as_float(m.y);
+        float4 v0, v1;
+        const bool hot = HOT && (m.x & 1);
+        if (hot || taken < n) {
+          const unsigned char* base = hot ? reinterpret_cast<const unsigned char*>(&s_hot[d][0])
+                                          : ring + slot * kSlot;
+          if (!hot) { ++taken; slot = slot + 1 == NS ? 0 : slot + 1; }
+          v0 = *reinterpret_cast<const float4*>(base + lane * 16);
+          v1 = ld1 ? *reinterpret_cast<const float4*>(base + 512 + lane * 16) : zero4();
+        } else {                                         // staged but not in the ring (long rows): direct gather
+          const char* a0 = (d ? pnb1 : pnb0) + lane * 16 + (uint32_t)(m.x & ~1);
+          v0 = ldg4(a0);
+          v1 = ld1 ? ldg4(a0 + 512) : zero4();
+        }
+        fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+      }
+      for (int i = max(beg, kTmaCap); i < end; ++i) {    // slow path: slice overflowed the staging buffer
+        const PnDir& dd = p.dir[d];
+        const int64_t e = (int64_t)ebase + i;
+        const float w = dd.w ? dd.w[e] : 1.0f;
+        const float c = w * (w * p.prior[dd.src[e]]);
+        const char* a = (d ? pnb1 : pnb0) + lane * 16 + (uint32_t)dd.rel[e] * (uint32_t)kPnRowBytes;
+        const float4 v0 = ldg4(a);
+        const float4 v1 = ld1 ? ldg4(a + 512) : zero4();
+        fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+      }
+      head_c += n; head_c = head_c >= NS ? head_c - NS : head_c;
+      used -= n;
+      const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);
+      const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int seg = d * SEGP + j * 2 * SEGP;
+        emit4(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
+        emit4(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
+      }
+    }
+    mbar_arrive(&s_empty[it & 1]);     // every consumer thread arrives (count = KW * 32)
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Ring kernel (gr_set_option("agg_abs_ws", 20)): three warp roles per CTA.
+//   stager  (1 warp)  : as in agg_abs_ws_kernel -- stages tile t+1 (row pointers, {table offset, coefficient} per edge,
+//                       relu(+-ins)/2) while tile t is processed.
+//   issuer  (1 warp)  : walks the staged tile in the consumers' order, one "block" (KW rows x both directions) at a
+//                       time, and issues one 1-D bulk copy (cp.async.bulk -> UBLKCP) per gathered edge: table row ->
+//                       next slot of a CTA-wide ring in shared memory; the block's mbarrier carries the byte count.
+//                       It also writes, per (row, direction) unit, {first ring slot, #ring edges} and the edge
+//                       coefficients in ring order.  It runs ahead of the consumers by as many blocks as fit in the
+//                       ring (reclaimed block by block through "empty" mbarriers).
+//   consumers (KW)    : one destination row per block each; wait for the block's bytes, accumulate S / Q from the ring
+//                       with LDS.128 (no global loads, no per-edge address arithmetic on 64-bit pointers), epilogue as
+//                       before.
+// Why: ncu on the LDG kernels (profiles/README.md) shows nothing saturated (L1TEX 57 %, issue 48 %, L2 41 %, DRAM 38 %)
+// and 58 % of the stall samples on the first use of gathered data; adding consumer warps does not help (18 warps:
+// -3 %; 22: +10 %; 28 half-row warps: +40 %) -- the LSU/L1 miss path cannot keep more gather requests in flight.  The
+// bulk copies bypass LSU and L1 and their number in flight is bounded by the ring size only.  A first version that
+// let every consumer warp issue its own copies (kept below as agg_abs_tma_kernel) removed the long-scoreboard stalls but
+// doubled the instruction count (bookkeeping + 8 instructions per copy for the lane -> uniform-register waterfall).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kRingUnitCap = 6;    // ring slots one (row, direction) unit may take; further staged edges use LDG
+constexpr int kChunks = 4;         // blocks in flight (mbarrier pairs)
+
+template <int NI, int KW>
+struct alignas(16) RingBuf {
+  int2 rc[2][kTmaCap];
+  float x[2][NI][2][kPnCols];
+  int32_t rowptr[2][KW * 8 + 4];
+  uint32_t ud[2][KW * 8];          // per unit: first ring slot | #ring edges << 16   (written by the issuer)
+  int32_t tile;
+  int32_t pad_[3];
+};
+
+template <int NI, int DT, int SEGP, int KW, int RS>
+__global__ void __launch_bounds__((KW + 2) * 32, 2) agg_abs_ring_kernel(const PnParams p, int ntiles) {
+  constexpr int ROWS = KW * 8;
+  constexpr int kSlot = DT * 4;
+  static_assert(DT % 4 == 0 && DT > 128 && DT <= kPnCols && RS >= 2 * KW * kRingUnitCap, "ring must hold a block");
+  using Buf = RingBuf<NI, KW>;
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  Buf* bufs = reinterpret_cast<Buf*>(ws_smem);
+  unsigned char* const ring = ws_smem + 2 * sizeof(Buf);
+  float* const ringc = reinterpret_cast<float*>(ring + (size_t)RS * kSlot);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];      // tile buffers (stager <-> issuer + consumers)
+  __shared__ __align__(8) uint64_t c_full[kChunks], c_empty[kChunks];   // ring blocks (issuer <-> consumers)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], (KW + 1) * 32); mbar_init(&s_empty[1], (KW + 1) * 32);
+    for (int c = 0; c < kChunks; ++c) { mbar_init(&c_full[c], 1); mbar_init(&c_empty[c], KW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == KW) {
+    // =============================== stager ===============================
+    for (int it = 0;; ++it) {
+      Buf& bf = bufs[it & 1];
+      if (it >= 2) mbar_wait(&s_empty[it & 1], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[it & 1]);
+        break;
+      }
+      produce_tile_rows<NI, DT, ROWS, kTmaCap>(bf, p, tile, lane);
+      __syncwarp();
+      mbar_arrive(&s_full[it & 1]);
+    }
+    return;
+  }
+
+  if (warp == KW + 1) {
+    // =============================== issuer ===============================
+    const char* const pnb0 = reinterpret_cast<const char*>(p.dir[0].pn);
+    const char* const pnb1 = reinterpret_cast<const char*>(p.dir[1].pn);
+    const uint32_t ring_s = smem_u32(ring);
+    uint32_t chunk_seq = 0, oldest = 0;
+    int head = 0, inflight = 0;
+    int size_hist = 0;                       // sizes of the <= kChunks blocks in flight, 8 bits each (lane-uniform)
+    for (int it = 0;; ++it) {
+      Buf& bf = bufs[it & 1];
+      mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+      const int tile = bf.tile;
+      if (tile < 0) break;
+      const int nrows = (int)min((int64_t)ROWS, p.Nt - (int64_t)tile * ROWS);
+      const int nblocks = (nrows + KW - 1) / KW;
+      const int eb0 = bf.rowptr[0][0], eb1 = bf.rowptr[1][0];
+      for (int b = 0; b < nblocks; ++b) {
+        // lane l < 2*KW describes unit (row b*KW + (l >> 1), direction l & 1)
+        const int ud_d = lane & 1, ud_row = b * KW + (lane >> 1);
+        int ubeg = 0, un = 0;
+        if (lane < 2 * KW && ud_row < nrows) {
+          const int ebase = ud_d ? eb1 : eb0;
+          ubeg = bf.rowptr[ud_d][ud_row] - ebase;
+          const int uend = bf.rowptr[ud_d][ud_row + 1] - ebase;
+          un = max(0, min(min(uend, kTmaCap) - ubeg, kRingUnitCap));
+        }
+        int incl = un;                        // inclusive prefix sum over the 2*KW unit lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int T = __shfl_sync(0xffffffffu, incl, 31);
+        const int ustart = incl - un;
+        // reclaim ring space / barrier slots of finished blocks
+        while (inflight + T > RS || chunk_seq - oldest >= (uint32_t)kChunks) {
+          mbar_wait(&c_empty[oldest % kChunks], (oldest / kChunks) & 1);
+          inflight -= (size_hist >> (8 * (oldest % kChunks))) & 0xff;
+          ++oldest;
+        }
+        const int ch = chunk_seq % kChunks;
+        size_hist = (size_hist & ~(0xff << (8 * ch))) | (T << (8 * ch));
+        uint64_t* const bar = &c_full[ch];
+        if (lane < 2 * KW && ud_row < nrows) {
+          int s0 = head + ustart;
+          s0 = s0 >= RS ? s0 - RS : s0;
+          bf.ud[ud_d][ud_row] = (uint32_t)s0 | ((uint32_t)un << 16);
+        }
+        // the copies: unit by unit, lane i = edge i of the unit
+#pragma unroll 1
+        for (int u = 0; u < 2 * KW; ++u) {
+          const int n = __shfl_sync(0xffffffffu, un, u);
+          if (n == 0) continue;
+          const int beg = __shfl_sync(0xffffffffu, ubeg, u);
+          const int st = __shfl_sync(0xffffffffu, ustart, u);
+          const int d = u & 1;
+          if (lane < n) {
+            const int2 m = bf.rc[d][beg + lane];
+            int slot = head + st + lane;
+            slot = slot >= RS ? slot - RS : slot;
+            ringc[slot] = __int_as_float(m.y);
+            bulk_g2s(ring_s + (uint32_t)(slot * kSlot), (d ? pnb1 : pnb0) + (uint32_t)m.x, (uint32_t)kSlot, bar);
+          }
+        }
+        // publish: the arrive (release) orders this warp's ud / ringc stores before the consumers' reads; the bytes of
+        // copies that already landed were counted negative and are balanced by the expect_tx
+        __syncwarp();
+        if (lane == 0) {
+          if (T > 0) mbar_expect_tx(bar, (uint32_t)(T * kSlot));
+          else mbar_arrive1(bar);
+        }
+        head += T; head = head >= RS ? head - RS : head;
+        inflight += T;
+        ++chunk_seq;
+      }
+      // this warp is done reading the tile buffer
+      mbar_arrive(&s_empty[it & 1]);
+    }
+    return;
+  }
+
+  // =============================== consumer warps ===============================
+  const bool ld1 = 128 + lane * 4 < DT;
+  const bool wr1 = 128 + lane * 4 < SEGP;
+  const char* const tb0 = reinterpret_cast<const char*>(p.dir[0].pn) + lane * 16;
+  const char* const tb1 = reinterpret_cast<const char*>(p.dir[1].pn) + lane * 16;
+  const unsigned char* const ring_lane = ring + lane * 16;
+  LaneIns<NI> x;
+  uint32_t chunk_seq = 0;
+  for (int it = 0;; ++it) {
+    Buf& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int64_t r0 = (int64_t)tile * ROWS;
+    const int nrows = (int)min((int64_t)ROWS, p.Nt - r0);
+    const int nblocks = (nrows + KW - 1) / KW;
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    __nv_bfloat16* const hi_lane = p.out_hi + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* const lo_lane = p.out_lo + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    int cur_q = -1;
+    for (int b = 0; b < nblocks; ++b, ++chunk_seq) {
+      const int lr = b * KW + warp;
+      const int ch = chunk_seq % kChunks;
+      if (lr < nrows) {
+        const int q = lr >= lr_switch ? 1 : 0;
+        if (q != cur_q) {
+          cur_q = q;
+          x.load(&bf.x[q][0][0][lane * 4]);
+        }
+        mbar_wait(&c_full[ch], (chunk_seq / kChunks) & 1);
+        __nv_bfloat16* const hrow = hi_lane + (int64_t)lr * p.ld;
+        __nv_bfloat16* const lrow = lo_lane + (int64_t)lr * p.ld;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const uint32_t desc = bf.ud[d][lr];
+          int slot = (int)(desc & 0xffffu);
+          const int n = (int)(desc >> 16);
+          float4 S0 = zero4(), S1 = S0, Q0 = S0, Q1 = S0;
+          float4 v1 = zero4();                               // lanes without chunk-1 columns never overwrite it
+          for (int i = 0; i < n; ++i) {
+            const unsigned char* a = ring_lane + slot * kSlot;
+            const float c = ringc[slot];
+            const float4 v0 = *reinterpret_cast<const float4*>(a);
+            if (ld1) v1 = *reinterpret_cast<const float4*>(a + 512);
+            slot = slot + 1 == RS ? 0 : slot + 1;
+            fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+          }
+          {                                                  // rows longer than the ring share / the staging buffer
+            const int ebase = bf.rowptr[d][0];
+            const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+            if (end - beg > n) {
+              const char* tb = d ? tb1 : tb0;
+              const int fast_end = min(end, kTmaCap);
+              for (int i = beg + n; i < fast_end; ++i) {
+                const int2 m = bf.rc[d][i];
+                const char* a0 = tb + (uint32_t)m.x;
+                const float4 v0 = ldg4(a0);
+                if (ld1) v1 = ldg4(a0 + 512);
+                const float c = __int_as_float(m.y);
+                fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+              }
+              const PnDir& dd = p.dir[d];
+              for (int i = max(beg + n, kTmaCap); i < end; ++i) {
+                const int64_t e = (int64_t)ebase + i;
+                const float w = dd.w ? dd.w[e] : 1.0f;
+                const float c = w * (w * p.prior[dd.src[e]]);
+                const char* a0 = tb + (uint32_t)dd.rel[e] * (uint32_t)kPnRowBytes;
+                const float4 v0 = ldg4(a0);
+                if (ld1) v1 = ldg4(a0 + 512);
+                fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+              }
+            }
+          }
+          const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);
+          const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            const int seg = d * SEGP + j * 2 * SEGP;
+            emit4(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
+            emit4(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&c_empty[ch]);               // this warp's ring slots of the block are free
+    }
+    mbar_arrive(&s_empty[it & 1]);
+  }
+}
+
+template <int NI, int KW, int RS>
+int launch_ring(const PnParams& p, cudaStream_t stream) {
+  auto kern = agg_abs_ring_kernel<NI, 200, 208, KW, RS>;
+  const size_t smem = 2 * sizeof(RingBuf<NI, KW>) + (size_t)RS * 200 * 4 + (size_t)RS * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+  const unsigned tiles = (unsigned)ceil_div(p.Nt, KW * 8);
+  const unsigned pgrid = std::min<unsigned>(tiles, 2u * (unsigned)sm_count());
+  kern<<<pgrid, (KW + 2) * 32, smem, stream>>>(p, (int)tiles);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
 // table [rows, D] fp32 (row stride ldt) -> zero-padded [rows][256]
 __global__ void pad_table_kernel(const float* __restrict__ table, int64_t ldt, int64_t rows, int D,
                                  float* __restrict__ out) {
@@ -446,9 +1456,77 @@ __global__ void pad_table_kernel(const float* __restrict__ table, int64_t ldt, i
   reinterpret_cast<float4*>(out + r * kPnCols)[g] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+template <int NI, int KW, int NS, int MINB, bool HOT>
+int launch_tma(const PnParams& p, unsigned grid, cudaStream_t stream) {
+  auto kern = agg_abs_tma_kernel<NI, 200, 208, KW, NS, MINB, HOT>;
+  const size_t smem = 2 * sizeof(TmaBuf<NI>) + (size_t)KW * NS * 200 * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+  const unsigned pgrid = std::min<unsigned>(grid, (unsigned)MINB * (unsigned)sm_count());
+  kern<<<pgrid, (KW + 1) * 32, smem, stream>>>(p, (int)grid);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
 template <int NI>
 int launch_pn(const PnParams& p, cudaStream_t stream) {
   const unsigned grid = (unsigned)ceil_div(p.Nt, kRows);
+  if (p.tile_counter && g_opt_agg_abs_ws >= 2 && g_opt_agg_abs_ws <= 5 && NI == 2) {
+    switch (g_opt_agg_abs_ws) {
+      case 2: return launch_tma<2, 8, 12, 2, false>(p, grid, stream);
+      case 3: return launch_tma<2, 8, 12, 2, true>(p, grid, stream);
+      case 4: return launch_tma<2, 16, 12, 1, true>(p, grid, stream);
+      default: return launch_tma<2, 12, 16, 1, true>(p, grid, stream);
+    }
+  }
+  if constexpr (NI == 2) {
+    if (p.tile_counter && g_opt_agg_abs_ws == 20) return launch_ring<2, 8, 96>(p, stream);
+    if (p.tile_counter && g_opt_agg_abs_ws >= 10) {
+      switch (g_opt_agg_abs_ws) {
+        case 10: return launch_wsg<2, 8, 64, 2>(p, stream);
+        case 11: return launch_wsg<2, 9, 72, 2>(p, stream);
+        case 12: return launch_wsg<2, 11, 66, 2>(p, stream);
+        case 13: return launch_wsg<2, 19, 76, 1>(p, stream);
+        case 14: return launch_wsg<2, 7, 56, 3>(p, stream);
+        default: return launch_wsg<2, 9, 63, 2>(p, stream);
+      }
+    }
+  }
+  if (p.tile_counter && g_opt_agg_abs_ws == 7 && NI <= 2) {
+    constexpr int SLOTS = 7, RPS = 8;
+    using Buf = HBuf<NI, SLOTS * RPS>;
+    auto kern = agg_abs_half_kernel<NI, 200, 208, SLOTS, RPS>;
+    const size_t smem = 2 * sizeof(Buf);
+    static bool attr_set = false;
+    if (!attr_set) {
+      GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+    const unsigned tiles = (unsigned)ceil_div(p.Nt, SLOTS * RPS);
+    const unsigned pgrid = std::min<unsigned>(tiles, 2u * (unsigned)sm_count());
+    kern<<<pgrid, (2 * SLOTS + 1) * 32, smem, stream>>>(p, (int)tiles);
+    GR_CHECK_LAUNCH();
+    return GR_OK;
+  }
+  if (p.tile_counter && g_opt_agg_abs_ws == 6) {
+    const size_t smem = 2 * sizeof(WsBuf<NI>);
+    static bool attr_set = false;
+    if (!attr_set) {
+      GR_CHECK_CUDA(cudaFuncSetAttribute(agg_abs_ws2_kernel<NI, 200, 208>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+    const unsigned pgrid = std::min<unsigned>(grid, 2u * (unsigned)sm_count());
+    agg_abs_ws2_kernel<NI, 200, 208><<<pgrid, kWsThreads, smem, stream>>>(p, (int)grid);
+    GR_CHECK_LAUNCH();
+    return GR_OK;
+  }
   if (p.tile_counter && g_opt_agg_abs_ws) {
     const size_t smem = 2 * sizeof(WsBuf<NI>);
     static bool attr_set = false;
@@ -511,6 +1589,7 @@ extern "C" int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   p.ld = ld_planes; p.out_col0 = out_col0; p.Nt = (int64_t)B * N;
   p.B = B; p.N = N; p.I = I; p.tile_counter = tile_counter;
+  p.hot_rel = g_opt_agg_hot_rel;
   for (int j0 = 0; j0 < I; j0 += 4) {
     p.j0 = j0;
     const int ni = I - j0 < 4 ? I - j0 : 4;

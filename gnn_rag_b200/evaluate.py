@@ -67,48 +67,90 @@ def f1_and_hits(answers, retrieved_ids):
 
 
 class Evaluator:
-    """Drop-in for ``gnn/evaluate.py:Evaluator`` (constructor :70-104, ``evaluate`` :140-240)."""
+    """Drop-in for ``gnn/evaluate.py:Evaluator`` (constructor :70-104, ``write_info`` :106-138, ``evaluate`` :140-240)."""
 
     def __init__(self, args, model, entity2id, relation2id, device):
         self.model, self.args, self.eps = model, args, args["eps"]
         self.model_name = args["model_name"]
         self.id2entity = {idx: ent for ent, idx in entity2id.items()}
         self.entity2name = None
+        if "sr-" in args.get("data_folder", ""):                   # gnn/evaluate.py:81-84
+            import pickle
+            with open("ent2id.pickle", "rb") as f:
+                self.entity2name = list(pickle.load(f).keys())
+        id2relation = {idx: rel for rel, idx in relation2id.items()}   # :87-101
+        num_rel_ori = len(relation2id)
+        if args.get("use_inverse_relation", False):
+            for i in range(len(id2relation)):
+                id2relation[i + num_rel_ori] = id2relation[i] + "_rev"
+        if args.get("use_self_loop", False):
+            id2relation[len(id2relation)] = "self_loop"
+        self.id2relation = id2relation
         self.device = device
         self.file_write = None
 
+    def _name(self, ent):
+        return self.id2entity[ent] if self.entity2name is None else self.entity2name[self.id2entity[ent]]
+
+    def write_info(self, valid_data, tp_list, num_step):
+        """One dict per question of the CURRENT batch (gnn/evaluate.py:106-138).  ``get_quest`` decodes the loader's
+        ``sample_ids``, which ``get_batch`` sets (gnn/dataset_load.py:130-141, 602-603): call it after every
+        ``get_batch`` and index the result by the position inside the batch."""
+        question_list = valid_data.get_quest()
+        obj_list = [{} for _ in question_list]
+        actions = None if tp_list is None else [tp[0] for tp in tp_list]
+        for j in range(num_step):
+            act = None if actions is None else actions[j].cpu().numpy()
+            for i, q in enumerate(question_list):
+                obj = obj_list[i]
+                obj["question"] = q
+                obj[j] = {}
+                if act is not None:
+                    obj[j]["rel_action"] = self.id2relation[act[i]]
+                    obj[j]["action"] = str(act[i])
+        return obj_list
+
     def evaluate(self, valid_data, test_batch_size=20, write_info=False):
+        write_info = True                                          # the reference forces it (gnn/evaluate.py:141)
         self.model.eval()
-        eps, id2entity = self.eps, self.id2entity
+        self.count = 0
+        eps = self.eps
         f1s, hits, ems, precisions, recalls = [], [], [], [], []
         valid_data.reset_batches(is_sequential=True)
         num_epoch = math.ceil(valid_data.num_data / test_batch_size)
         if write_info and self.file_write is None:
             path = os.path.join(self.args["checkpoint_dir"], "{}_test.info".format(self.args["experiment_name"]))
             self.file_write = open(path, "w")
-        questions = valid_data.get_quest() if write_info else None
-        num_entity = len(id2entity)
-        row = 0
+        case_ct = {}
+        num_entity = len(self.id2entity)
         for it in range(num_epoch):
             batch = valid_data.get_batch(it, test_batch_size, fact_dropout=0.0, test=True)
             answer_lists = batch[-1]
             with torch.no_grad():
-                _loss, _pred, pred_dist, _ = self.model(batch[:-1])
+                _loss, _pred, pred_dist, tp_list = self.model(batch[:-1])
+            # the reference drops candidates below (1 - eps) / valid_data.max_local_entity (:154); the ranking kernel
+            # uses the batch's own N, which is the loader's max_local_entity by construction (dataset_load.py:250)
+            mle = getattr(valid_data, "max_local_entity", pred_dist.shape[1])
+            if mle != pred_dist.shape[1]:
+                raise ValueError("batch width %d != valid_data.max_local_entity %d" % (pred_dist.shape[1], mle))
+            obj_list = self.write_info(valid_data, tp_list, self.model.num_iter) if write_info else None
             retrieved, _ = retrieve(pred_dist, self.model.last_batch, num_entity, eps)
             for b, ret in enumerate(retrieved):
                 answers = list(answer_lists[b])
-                ids = ret.ent.tolist()
-                p, r, f1, hit, em, _case = f1_and_hits(answers, ids)
+                p, r, f1, hit, em, case = f1_and_hits(answers, ret.ent.tolist())
                 if write_info:
-                    obj = {"question": questions[row]}
-                    for j in range(self.model.num_iter):
-                        obj[j] = {}
-                    obj.update({"answers": [id2entity[a] for a in answers], "precison": p, "recall": r,
-                                "f1": f1, "hit": hit, "em": em,
-                                "cand": [(id2entity[c], pr) for c, pr in ret.pairs()]})
+                    obj = obj_list[b]
+                    obj["answers"] = [self._name(a) for a in answers]
+                    obj["precison"] = p
+                    obj["recall"] = r
+                    obj["f1"] = f1
+                    obj["hit"] = hit
+                    obj["em"] = em
+                    obj["cand"] = [(self._name(c), pr) for c, pr in ret.pairs()]
                     self.file_write.write(json.dumps(obj) + "\n")
-                row += 1
+                case_ct[case] = case_ct.get(case, 0) + 1
                 f1s.append(f1); hits.append(hit); ems.append(em); precisions.append(p); recalls.append(r)
+        self.case_ct = case_ct
         if write_info and self.file_write is not None:
             self.file_write.close()
             self.file_write = None

@@ -8,15 +8,18 @@ gnn/train_model.py:236-252) and config keys (gnn/parsing.py) -- so the module dr
   ReaRev      gnn/models/ReaRev/rearev.py:19-244
   NSM         gnn/models/NSM/nsm.py:19-254
 
-Inference only: ``training=True`` needs autograd through the CUDA kernels and raises.
+``model(batch)`` runs the hand-written CUDA path; ``model(batch, training=True)`` -- what ``Trainer_KBQA.train_epoch``
+calls (gnn/train_model.py:222) -- evaluates the same math with differentiable torch ops on the same parameters
+(autograd_path.py) and returns ``tp_list = [h1, f1]`` like the reference (rearev.py:238-241), so the import swap of
+INTEGRATION.md leaves training working.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import batching, ops
-from .modules import (AttnEncoder, Fusion, LSTMInstruction, NSMLayer, QueryReform, ReasonGNNLayer,
+from . import autograd_path, batching, ops
+from .modules import (AttnEncoder, BERTInstruction, Fusion, LSTMInstruction, NSMLayer, QueryReform, ReasonGNNLayer,
                       TypeLayer)
 
 VERY_SMALL_NUMBER = 1e-10
@@ -106,12 +109,20 @@ class BaseModel(nn.Module):
             self.rel_features = self.instruction.encode_question(self.rel_texts, store=False)
             self.rel_features_inv = self.instruction.encode_question(self.rel_texts_inv, store=False)
 
-    def _make_instruction(self, args):
-        if args["lm"] != "lstm":
+    def _make_instruction(self, args):                             # rearev.py:121-127 / nsm.py:70-76
+        if args["lm"] == "lstm":
+            return LSTMInstruction(args, self.word_embedding, self.num_word)
+        return BERTInstruction(args, self.word_embedding, self.num_word, args["lm"])
+
+    def _rel_text_features(self, raw, texts, att):
+        """Relation-text branch of get_rel_feature (rearev.py:100-111 / nsm.py:104-111): project the stored encoder
+        states of the relation names and pool them with ``att`` over the non-pad tokens."""
+        ins = self.instruction
+        if not hasattr(ins, "question_emb"):
             raise NotImplementedError(
-                "lm=%r needs a HuggingFace encoder download (bert_encoder.py:31-78); this build ships the "
-                "LSTM question encoder only" % args["lm"])
-        return LSTMInstruction(args, self.word_embedding, self.num_word)
+                "relation_word_emb needs a language-model encoder (--lm sbert/bert/...): with --lm lstm the reference "
+                "itself fails here (LSTMInstruction has no question_emb, rearev.py:101)")
+        return att(ins.question_emb(raw), (texts != ins.pad_val).float())
 
     def _get_ent_init(self, db, rel_features, layer):              # rearev.py:79-88 / nsm.py:84-94
         """Initial node embeddings, written straight into the reasoning layer's h slot(s)."""
@@ -151,11 +162,7 @@ class BaseModel(nn.Module):
         case_valid = (torch.sum(answer_dist, dim=1, keepdim=True) > 0).float()
         return self.calc_loss_label(pred_dist, answer_dist, case_valid), torch.max(pred_dist, dim=1)[1]
 
-    def _check_ready(self, training):
-        if training:
-            raise NotImplementedError(
-                "gnn_rag_b200 implements the inference forward (forward + score); training needs the "
-                "backward of the aggregation kernel (SURVEY.md 8f row 4) -- train with the reference")
+    def _check_ready(self):
         dev = self.word_embedding.weight.device
         if dev.type != "cuda":
             raise RuntimeError("gnn_rag_b200 models run on a CUDA device only (no CPU fallback); "
@@ -193,18 +200,28 @@ class ReaRev(BaseModel):
             lin = self.relation_linear
             return ops.rel_features_from_embeddings(
                 [self.relation_embedding.weight, self.relation_embedding_inv.weight], lin.weight, lin.bias)
-        ins = self.instruction
-        rel = ins.question_emb(self.rel_features)
-        rel_inv = ins.question_emb(self.rel_features_inv)
-        rel = self.self_att_r(rel, (self.rel_texts != ins.pad_val).float())
-        rel_inv = self.self_att_r(rel_inv, (self.rel_texts != ins.pad_val).float())
-        return ops.rel_features_from_tensors([rel, rel_inv])
+        rel, rel_inv = self.get_rel_feature_train()
+        return ops.rel_features_from_tensors([rel.contiguous(), rel_inv.contiguous()])
 
-    @torch.no_grad()
+    def get_rel_feature_train(self):
+        """(rel_features, rel_features_inv) as plain fp32 tensors with autograd (rearev.py:91-111)."""
+        if self.rel_texts is None:
+            lin = self.relation_linear
+            return lin(self.relation_embedding.weight), lin(self.relation_embedding_inv.weight)
+        # both directions are masked with rel_texts, as in the reference (:104-105)
+        return (self._rel_text_features(self.rel_features, self.rel_texts, self.self_att_r),
+                self._rel_text_features(self.rel_features_inv, self.rel_texts, self.self_att_r))
+
     def forward(self, batch, training=False):
         """rearev.py:163-243.  ``batch`` = the ``get_batch`` tuple (host numpy) or a pre-staged
-        :class:`batching.DeviceBatch`."""
-        dev = self._check_ready(training)
+        :class:`batching.DeviceBatch`.  ``training=True``: differentiable torch path (autograd_path.py)."""
+        if training:
+            return autograd_path.rearev_forward(self, batch)
+        with torch.no_grad():
+            return self._forward_infer(batch)
+
+    def _forward_infer(self, batch):
+        dev = self._check_ready()
         D, I = self.entity_dim, self.num_ins
         db = batching.stage_batch(batch, dev, self.num_relation + 1, self.normalized_gnn, self.norm_rel)
         self.last_batch = db
@@ -261,13 +278,25 @@ class NSM(BaseModel):
         self.to(self.device)
 
     def get_rel_feature(self):                                   # nsm.py:97-111
-        lin = self.relation_linear1
-        return ops.rel_features_from_embeddings([self.relation_embedding.weight], lin.weight, lin.bias)
+        if self.rel_texts is None:
+            lin = self.relation_linear1
+            return ops.rel_features_from_embeddings([self.relation_embedding.weight], lin.weight, lin.bias)
+        return ops.rel_features_from_tensors([self.get_rel_feature_train().contiguous()])
 
-    @torch.no_grad()
+    def get_rel_feature_train(self):
+        if self.rel_texts is None:
+            return self.relation_linear1(self.relation_embedding.weight)
+        return self._rel_text_features(self.rel_features, self.rel_texts, self.self_att_r)
+
     def forward(self, batch, training=False):
-        """nsm.py:179-254 (forward reasoning only)."""
-        dev = self._check_ready(training)
+        """nsm.py:179-254 (forward reasoning only).  ``training=True``: differentiable torch path."""
+        if training:
+            return autograd_path.nsm_forward(self, batch)
+        with torch.no_grad():
+            return self._forward_infer(batch)
+
+    def _forward_infer(self, batch):
+        dev = self._check_ready()
         db = batching.stage_batch(batch, dev, self.num_relation + 1, self.normalized_gnn, self.norm_rel)
         self.last_batch = db
         rel_f = self.get_rel_feature()

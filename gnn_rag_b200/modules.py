@@ -103,6 +103,18 @@ class LSTMInstruction(nn.Module):
         self.ca_linear = nn.Linear(D, 1)
         for i in range(self.num_ins):
             self.add_module("question_linear" + str(i), nn.Linear(D, D))
+        self.lstm_drop = nn.Dropout(p=args.get("lm_dropout", 0.0))        # base_encoder.py:49-52
+        self.linear_drop = nn.Dropout(p=args.get("linear_dropout", 0.0))
+        self.pad_val = num_word
+
+    def encode_question_train(self, query_text):
+        """lstm_encoder.py:32-45 with autograd (cuDNN / torch LSTM) -- the training path of autograd_path.py."""
+        emb = self.lstm_drop(self.word_embedding(query_text))
+        z = torch.zeros(1, query_text.size(0), self.entity_dim, device=emb.device, dtype=emb.dtype)
+        hidden, (h_n, _c) = self.node_encoder(emb, (z, z.clone()))
+        self.query_hidden_emb = hidden
+        self.query_node_emb = h_n.squeeze(0).unsqueeze(1)
+        self.query_mask_train = (query_text != self.num_word).float()
 
     def encode_question(self, query_text, store=True):
         emb = self.word_embedding(query_text)
@@ -148,6 +160,110 @@ class LSTMInstruction(nn.Module):
         lins = [getattr(self, "question_linear" + str(i)) for i in range(I)]
         ins = ops.instructions(self.query_hidden_emb, self.query_node_emb.squeeze(1), query_text, self.num_word,
                                [l.weight for l in lins], [l.bias for l in lins], self.cq_linear.weight,
+                               self.cq_linear.bias, self.ca_linear.weight.view(-1), self.ca_linear.bias)
+        self.relational_ins = ins[:, I - 1]
+        return ins
+
+
+# HuggingFace encoder variants of BERTInstruction (bert_encoder.py:29-60): name -> (hub id, config class, config
+# overrides, word_dim, pad token id).  The architectures are fixed by the hub ids, so the encoder can be BUILT offline
+# from its config; a published checkpoint then fills ``instruction.node_encoder.*`` through load_state_dict.
+_LM_SPECS = {
+    "bert": ("bert-base-uncased", "BertConfig", {}, 768, 0),
+    "simcse": ("princeton-nlp/sup-simcse-bert-base-uncased", "BertConfig", {}, 768, 0),
+    "relbert": ("pretrained_lms/sr-simbert/", "BertConfig", {}, 768, 0),
+    "sbert": ("sentence-transformers/all-MiniLM-L6-v2", "BertConfig",
+              dict(hidden_size=384, num_hidden_layers=6, num_attention_heads=12, intermediate_size=1536), 384, 0),
+    "roberta": ("roberta-base", "RobertaConfig",
+                dict(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, pad_token_id=1,
+                     bos_token_id=0, eos_token_id=2, layer_norm_eps=1e-5), 768, 1),
+    "sbert2": ("sentence-transformers/all-mpnet-base-v2", "MPNetConfig", dict(vocab_size=30527), 768, 1),
+}
+
+
+class BERTInstruction(nn.Module):
+    """Language-model question encoder (bert_encoder.py:18-108) + the shared instruction attention
+    (base_encoder.py:73-114).  Same parameter names as the reference (``node_encoder.*`` is the HuggingFace model,
+    ``question_emb``, ``cq_linear``, ``ca_linear``, ``question_linear{i}``), so ``--lm sbert`` checkpoints load.
+
+    The reference downloads tokenizer + weights from the hub at construction (:31-60,72).  Here the encoder is
+    loaded from the local HuggingFace cache when it is there (``local_files_only``) and otherwise built from the
+    architecture's config with random weights, to be filled by ``load_state_dict``; ``args['lm_config']`` (dict of
+    config overrides, e.g. a 2-layer test model) takes precedence.  The transformer itself runs in PyTorch: it is
+    the INPUT of the graph path; the instruction attention runs in csrc/question.cu."""
+
+    def __init__(self, args, word_embedding, num_word, model):
+        super().__init__()
+        if model not in _LM_SPECS:
+            raise NotImplementedError("lm=%r: supported language-model encoders are %s (t5 is an encoder-decoder "
+                                      "the reference special-cases, bert_encoder.py:86-89)" % (model, sorted(_LM_SPECS)))
+        if "num_step" in args:                       # base_encoder.py:24-33
+            self.num_ins = args["num_step"]
+        elif "num_ins" in args:
+            self.num_ins = args["num_ins"]
+        else:
+            self.num_ins = 1
+        self.model = model
+        self.entity_dim = D = args["entity_dim"]
+        self.word_embedding = word_embedding
+        self.num_word = num_word
+        self.lm_frozen = args.get("lm_frozen", 1)
+        hub_id, cfg_cls, overrides, word_dim, pad = _LM_SPECS[model]
+        self.pretrained_weights = hub_id
+        self.word_dim = word_dim
+        self.pad_val = pad
+        self.cq_linear = nn.Linear(4 * D, D)
+        self.ca_linear = nn.Linear(D, 1)
+        for i in range(self.num_ins):
+            self.add_module("question_linear" + str(i), nn.Linear(D, D))
+        self.question_emb = nn.Linear(word_dim, D)
+        self.lstm_drop = nn.Dropout(p=args.get("lm_dropout", 0.0))
+        self.linear_drop = nn.Dropout(p=args.get("linear_dropout", 0.0))
+        self.node_encoder = self._build_encoder(hub_id, cfg_cls, overrides, args.get("lm_config"))
+        if self.node_encoder.config.hidden_size != word_dim:
+            self.word_dim = self.node_encoder.config.hidden_size
+            self.question_emb = nn.Linear(self.word_dim, D)
+        for prm in self.node_encoder.parameters():                       # bert_encoder.py:74-81
+            prm.requires_grad = self.lm_frozen != 1
+
+    @staticmethod
+    def _build_encoder(hub_id, cfg_cls, overrides, user_cfg):
+        import transformers
+        if user_cfg is None:
+            try:
+                return transformers.AutoModel.from_pretrained(hub_id, local_files_only=True)
+            except Exception:  # noqa: BLE001 -- not in the local cache: build the architecture, weights come from the ckpt
+                pass
+        cfg = getattr(transformers, cfg_cls)(**dict(overrides, **(user_cfg or {})))
+        return transformers.AutoModel.from_config(cfg)
+
+    def _hidden(self, query_text):
+        return self.node_encoder(query_text)[0]                          # bert_encoder.py:86 (no attention mask)
+
+    def encode_question(self, query_text, store=True):                   # bert_encoder.py:83-105
+        raw = self._hidden(query_text)
+        if not store:
+            return raw
+        self.query_hidden_emb = self.question_emb(raw)
+        self.query_node_emb = self.question_emb(raw[:, 0].unsqueeze(1))
+        self._query_text = query_text
+        return raw, self.query_node_emb
+
+    def encode_question_train(self, query_text):
+        self.encode_question(query_text)
+        self.query_mask_train = (query_text != self.pad_val).float()
+
+    @property
+    def query_mask(self):
+        return (self._query_text != self.pad_val).float()
+
+    def forward(self, query_text):
+        """-> instructions [B, num_ins, D]; the LM runs in torch, the attention steps in one kernel launch."""
+        self.encode_question(query_text)
+        I = self.num_ins
+        lins = [getattr(self, "question_linear" + str(i)) for i in range(I)]
+        ins = ops.instructions(self.query_hidden_emb.contiguous(), self.query_node_emb.squeeze(1), query_text,
+                               self.pad_val, [l.weight for l in lins], [l.bias for l in lins], self.cq_linear.weight,
                                self.cq_linear.bias, self.ca_linear.weight.view(-1), self.ca_linear.bias)
         self.relational_ins = ins[:, I - 1]
         return ins
@@ -247,6 +363,7 @@ class ReasonGNNLayer(_GraphLayerBase):
                 self.add_module("pos_emb" + str(i), nn.Embedding(num_relation, D))
                 self.add_module("pos_emb_inv" + str(i), nn.Embedding(num_relation, D))
         self.lin_m = nn.Linear(self.num_ins * D, D)           # unused in forward
+        self.linear_drop_train = nn.Dropout(p=args.get("linear_dropout", 0.0))   # reasongnn.py:34-35 (training path)
 
     def init_reason(self, db, rel_features):
         """reasongnn.py:46-58.  Also builds the hoisted per-layer relation tables
@@ -328,6 +445,7 @@ class NSMLayer(_GraphLayerBase):
         for i in range(self.num_steps):
             self.add_module("rel_linear" + str(i), nn.Linear(D, D))
             self.add_module("e2e_linear" + str(i), nn.Linear(2 * D, D))
+        self.linear_drop_train = nn.Dropout(p=args.get("linear_dropout", 0.0))   # nsm_gnn.py:30-31 (training path)
 
     def init_reason(self, db, rel_features):
         D = self.entity_dim

@@ -83,22 +83,39 @@ def test_nsm_webqsp_shape_vs_oracle_and_reason_kb():
 
 
 class _FakeLoader:
-    """Just enough of SingleDataLoader (gnn/dataset_load.py:599-629) for Evaluator.evaluate."""
+    """SingleDataLoader's batching contract (gnn/dataset_load.py:599-629, 130-141): ``get_batch`` slices
+    ``self.batches[start:end]`` into ``self.sample_ids``; ``get_quest`` decodes ONLY those and does not exist as a
+    usable call before the first ``get_batch`` (no ``sample_ids`` attribute yet)."""
 
-    def __init__(self, B, N, E, num_batches):
-        self.num_data, self.bs = B * num_batches, B
+    def __init__(self, B, N, E, num_data):
+        self.num_data = num_data
         self.max_local_entity = N
-        self.batches = [S.make_batch(20 + i, B=B, N=N, E=E, num_entity=500, num_relation=30, num_word=60,
-                                     test=True, with_weights=False) for i in range(num_batches)]
+        self.data = S.make_batch(20, B=num_data, N=N, E=E, num_entity=500, num_relation=30, num_word=60,
+                                 test=True, with_weights=False)
+        self.N = N
+        self.batches = np.arange(num_data)
 
     def reset_batches(self, is_sequential=True):
-        pass
+        self.batches = np.arange(self.num_data)
 
     def get_quest(self):
-        return ["question %d " % i for i in range(self.num_data)]
+        return ["question %d " % i for i in self.sample_ids]      # AttributeError before the first get_batch
 
-    def get_batch(self, iteration, batch_size, fact_dropout, test=False):
-        return self.batches[iteration]
+    def get_batch(self, iteration, batch_size, fact_dropout, q_type=None, test=False):
+        start, end = batch_size * iteration, min(batch_size * (iteration + 1), self.num_data)
+        ids = self.batches[start:end]
+        self.sample_ids = ids
+        le, qe, kb, qi, sd, _, ad, al = self.data
+        heads, rels, tails, bids = kb[0], kb[1], kb[2], kb[3]
+        sel = np.isin(bids, ids)
+        remap = -np.ones(self.num_data, dtype=np.int64)
+        remap[ids] = np.arange(len(ids))
+        nb = remap[bids[sel]]
+        h = heads[sel] - bids[sel] * self.N + nb * self.N
+        t = tails[sel] - bids[sel] * self.N + nb * self.N
+        kb2 = (h, rels[sel], t, nb, np.arange(len(h)), None, None)
+        out = (le[ids], qe[ids], kb2, qi[ids], sd[ids], None, ad[ids])
+        return out + (al[ids],) if test else out
 
 
 def test_info_jsonl_matches_shipped_schema(tmp_path):
@@ -113,10 +130,11 @@ def test_info_jsonl_matches_shipped_schema(tmp_path):
         m.reasoning.score_func.weight.mul_(30.0)
     entity2id = {"m.%04d" % i: i for i in range(500)}
     ev = G.Evaluator(args, m, entity2id, {}, torch.device(DEV))
-    loader = _FakeLoader(B=4, N=64, E=200, num_batches=2)
+    loader = _FakeLoader(B=4, N=64, E=200, num_data=10)          # 10 questions, batches of 4: 4 + 4 + 2
     f1, h1, em = ev.evaluate(loader, test_batch_size=4, write_info=True)
     rows = [json.loads(l) for l in open(os.path.join(str(tmp_path), "t_test.info"))]
-    assert len(rows) == 8 and 0.0 <= f1 <= 1.0
+    assert len(rows) == 10 and 0.0 <= f1 <= 1.0
+    assert [r["question"] for r in rows] == ["question %d " % i for i in range(10)]   # per-batch get_quest, in order
     for r in rows:
         assert list(r.keys()) == list(sample[0].keys())               # same keys, same order
         for k, v in sample[0].items():
@@ -125,7 +143,7 @@ def test_info_jsonl_matches_shipped_schema(tmp_path):
         probs = [c[1] for c in r["cand"]]
         assert probs == sorted(probs, reverse=True)
     # metrics agree with the reference's formula (oracle f1_and_hits) on the same retrieved lists
-    b = loader.batches[0]
+    b = loader.get_batch(0, 4, 0.0, test=True)
     _, _, dist, _ = m(b[:-1])
     ret, _ = evaluate.retrieve(dist, m.last_batch, 500, args["eps"])
     for q in range(4):

@@ -1,0 +1,74 @@
+"""``model(batch, training=True)`` -- the call of Trainer_KBQA.train_epoch (gnn/train_model.py:222) -- against loss,
+train-time metrics and parameter gradients recorded from the UNMODIFIED reference (tests/golden/train/*.npz, made by
+tests/golden/make_train_golden.py).  The differentiable path is plain torch, so it is checked on CPU tensors here
+(the product's inference path stays CUDA-only) and on the GPU in test_configs_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gnn_rag_b200 as G
+from golden_io import GOLDEN_DIR, Golden
+
+CASES = ["rearev_small", "rearev_norm", "rearev_posemb", "rearev_sharp_ties", "nsm_small", "nsm_reason_kb"]
+
+
+def _load(name, device="cpu"):
+    g = Golden(name)
+    t = np.load(os.path.join(GOLDEN_DIR, "train", name + ".npz"))
+    args = dict(g.args, use_cuda=(device != "cpu"))
+    cls = G.ReaRev if args["model_name"] == "ReaRev" else G.NSM
+    m = cls(args, g.num_entity, g.num_relation, g.num_word)
+    m.load_state_dict(g.sd, strict=True)
+    m.eval()                                            # dropout = identity, as in the generator
+    batch = list(g.batch[:7])
+    batch[6] = t["answer_dist"]
+    return m, tuple(batch), t
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_training_forward_backward_matches_reference(name):
+    m, batch, t = _load(name)
+    loss, pred, pred_dist, tp_list = m(batch, training=True)
+    assert abs(float(loss.detach()) - float(t["loss"])) <= 2e-5 * abs(float(t["loss"]))
+    np.testing.assert_allclose(pred_dist.detach().numpy(), t["pred_dist"], rtol=2e-4, atol=1e-9)
+    assert torch.equal(pred, pred_dist.argmax(1))
+    h1, f1 = tp_list                                   # rearev.py:238-241: [h1.tolist(), f1.tolist()]
+    assert h1 == t["h1"].tolist()
+    np.testing.assert_allclose(np.array(f1), t["f1"], rtol=1e-6)
+    loss.backward()
+    checked = 0
+    for k, p in m.named_parameters():
+        key = "grad/" + k
+        if key not in t.files:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        want = t[key]
+        got = p.grad.numpy() if p.grad is not None else np.zeros_like(want)
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 2e-4 * scale + 5e-9, (k, np.abs(got - want).max(), scale)   # 5e-9: the
+        # score bias has a mathematically zero gradient (softmax is shift invariant), both sides hold rounding noise
+        checked += 1
+    assert checked >= 20
+
+
+def test_two_adam_steps_reduce_the_loss():
+    """The INTEGRATION.md import swap leaves Trainer_KBQA.train_epoch's inner loop working
+    (gnn/train_model.py:219-231): forward(training=True) -> backward -> clip -> Adam step."""
+    m, batch, _ = _load("rearev_small")
+    m.train()
+    torch.manual_seed(0)
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=5e-3)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss, _, _, tp_list = m(batch, training=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in m.parameters()], 1.0)
+        opt.step()
+        losses.append(float(loss))
+        assert len(tp_list) == 2 and len(tp_list[0]) == batch[0].shape[0]
+    m.eval()
+    final = float(m(batch, training=True)[0])
+    assert final < losses[0]
