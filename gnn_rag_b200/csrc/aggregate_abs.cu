@@ -25,9 +25,11 @@
 //     single-edge tail.
 //   * output: the split-bf16 planes of the e2e GEMM's A operand, segment pitch SEGP (32-byte sectors, see
 //     aggregate.cu); columns D..SEGP-1 receive exact zeros (staged ins are zero there).
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -35,6 +37,7 @@ namespace gr {
 
 int g_opt_agg_abs_ws = 1;     // gr_set_option("agg_abs_ws", 0|1|2..): persistent warp-specialised kernel when a tile counter is given;
                               // >= 2: TMA-gather variants (agg_abs_tma_kernel)
+int g_opt_agg_table_rows = 0;  // experiment plumbing: rows of the padded tables for the gather4 tensor maps
 int g_opt_agg_hot_rel = -1;   // gr_set_option("agg_hot_rel", id): relation row kept resident by the TMA-gather kernel
 
 namespace {
@@ -64,6 +67,7 @@ struct PnParams {
   int B, N, I, j0;
   int32_t* tile_counter;   // persistent kernel: dynamic tile scheduler (zeroed before the launch)
   int hot_rel;             // TMA-gather kernel: relation whose table row stays resident in shared memory (-1: none)
+  int64_t table_rows;      // rows of each padded relation table (R1): the gather4 tensor maps need the extent
 };
 
 __device__ __forceinline__ float4 ldg4(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -309,8 +313,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity), "r"(20000u)     // suspend-time hint [ns]: an idle role polls rarely
-        : "memory");
+        : "r"(smem_u32(b)), "r"(parity), "r"(20000u)     // suspend-time hint [ns]: a waiting role does not spin on the
+        : "memory");                                       // issue port (measured: 129 us with, 141 us without)
   }
 }
 
@@ -627,7 +631,7 @@ struct alignas(16) HBuf {
   int32_t pad_[3];
 };
 
-template <int NI, int DT, int ROWS, int CAP = kEdgeCap, class Buf>
+template <int NI, int DT, int ROWS, int CAP = kEdgeCap, bool REL_INDEX = false, class Buf>
 __device__ __forceinline__ void produce_tile_rows(Buf& bf, const PnParams& p, int tile, int lane) {
   // The producer is ONE warp running dependent global loads (row pointers -> src / rel slices -> prior[src]); what
   // bounds it is the number of round trips per tile, not the instruction count.  Both directions and up to 8 edges
@@ -686,7 +690,7 @@ __device__ __forceinline__ void produce_tile_rows(Buf& bf, const PnParams& p, in
         const int i = i0 + lane + 32 * u;
         if (i < ne[d]) {
           const float w = (has_w && dd.w) ? __ldg(dd.w + eb[d] + i) : 1.0f;
-          bf.rc[d][i] = make_int2((int)((uint32_t)ridx[d][u] * (uint32_t)kPnRowBytes),
+          bf.rc[d][i] = make_int2(REL_INDEX ? ridx[d][u] : (int)((uint32_t)ridx[d][u] * (uint32_t)kPnRowBytes),
                                   __float_as_int(w * (w * pr[d][u])));
         }
       }
@@ -1443,6 +1447,952 @@ int launch_ring(const PnParams& p, cudaStream_t stream) {
   return GR_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-gather kernel, second version (gr_set_option("agg_abs_ws", 30)): per-warp double-buffered stages.
+//
+// scripts/micro/gather_bw.cu (profiles/r2_gather_bw.txt): random 800-byte rows of the L2-resident table are gathered
+// at 10 TB/s by 16 warps/SM of LDG.128 (independent of the loads in flight per warp), 16 TB/s by 32 warps/SM -- and at
+// 15.7 TB/s by 16 warps/SM that issue one cp.async.bulk per row into shared memory.  The aggregation kernel cannot
+// have 32 warps (96 registers), so the gather moves to the bulk-copy path and the kernel becomes issue-bound: the
+// whole design below is about instructions per (row, direction) unit.
+//   * every consumer warp owns two stages of NSS slots (800 B each) and one mbarrier per stage; while it accumulates
+//     unit g from stage g & 1 the copies of unit g + 1 are in flight into the other stage (fixed distance 1: no ring
+//     bookkeeping).  Lane i issues the copy of edge i (ptxas serialises the lanes through ELECT / R2UR: UBLKCP takes
+//     uniform registers, ~8 instructions per copy).
+//   * the accumulation loop is unrolled over the NSS slots: every shared-memory address is the lane's stage base plus
+//     an immediate, coefficients are LDS.32 broadcasts; rows with more staged edges than NSS finish through LDG.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kStageSlots = 6;
+
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds1(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+
+template <int NI, int DT, int SEGP, int KW, int ROWS>
+__global__ void __launch_bounds__((KW + 1) * 32, 2) agg_abs_tma2_kernel(const PnParams p, int ntiles) {
+  static_assert(DT % 4 == 0 && DT > 128 && DT <= kPnCols, "two column chunks of 128");
+  constexpr int NSS = kStageSlots;
+  constexpr int kSlot = DT * 4;
+  struct alignas(16) Buf {
+    int2 rc[2][kTmaCap];
+    float x[2][NI][2][kPnCols];
+    int32_t rowptr[2][ROWS + 4];
+    int32_t tile;
+    int32_t pad_[3];
+  };
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  Buf* bufs = reinterpret_cast<Buf*>(ws_smem);
+  unsigned char* const ring_all = ws_smem + 2 * sizeof(Buf);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  __shared__ __align__(8) uint64_t s_bar[KW][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], KW * 32); mbar_init(&s_empty[1], KW * 32);
+    for (int w = 0; w < KW; ++w) { mbar_init(&s_bar[w][0], 1); mbar_init(&s_bar[w][1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == KW) {
+    for (int it = 0;; ++it) {
+      Buf& bf = bufs[it & 1];
+      if (it >= 2) mbar_wait(&s_empty[it & 1], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[it & 1]);
+        break;
+      }
+      produce_tile_rows<NI, DT, ROWS, kTmaCap>(bf, p, tile, lane);
+      __syncwarp();
+      mbar_arrive(&s_full[it & 1]);
+    }
+    return;
+  }
+
+  // =============================== consumer warps ===============================
+  const bool ld1 = 128 + lane * 4 < DT;
+  const bool wr1 = 128 + lane * 4 < SEGP;
+  const char* const pnb0 = reinterpret_cast<const char*>(p.dir[0].pn);
+  const char* const pnb1 = reinterpret_cast<const char*>(p.dir[1].pn);
+  const uint32_t stage_s = smem_u32(ring_all) + (uint32_t)warp * 2u * NSS * kSlot;   // this warp's two stages
+  const uint32_t stage_lane = stage_s + lane * 16;
+  uint64_t* const bars = s_bar[warp];
+  LaneIns<NI> x;
+  uint32_t g = 0;                                             // units issued by this warp so far (stage = g & 1)
+
+  for (int it = 0;; ++it) {
+    Buf& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int64_t r0 = (int64_t)tile * ROWS;
+    const int nrows = (int)min((int64_t)ROWS, p.Nt - r0);
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    __nv_bfloat16* const hi_lane = p.out_hi + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* const lo_lane = p.out_lo + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    const int nunits = warp < nrows ? 2 * ((nrows - warp + KW - 1) / KW) : 0;
+    const int eb0 = bf.rowptr[0][0], eb1 = bf.rowptr[1][0];
+    const uint32_t rc_s = smem_u32(&bf.rc[0][0]);
+
+    // issue the bulk copies of unit u (first <= NSS staged edges) into stage gi & 1; returns beg | n << 16
+    auto issue = [&](int u, uint32_t gi, int& beg, int& end) -> int {
+      const int d = u & 1, lr = warp + KW * (u >> 1);
+      const int ebase = d ? eb1 : eb0;
+      beg = bf.rowptr[d][lr] - ebase;
+      end = bf.rowptr[d][lr + 1] - ebase;
+      const int n = max(0, min(min(end, kTmaCap) - beg, NSS));
+      uint64_t* const bar = &bars[gi & 1];
+      if (lane == 0) {
+        if (n > 0) mbar_expect_tx(bar, (uint32_t)(n * kSlot));
+        else mbar_arrive1(bar);
+      }
+      if (lane < n) {
+        const int off = bf.rc[d][beg + lane].x;
+        bulk_g2s(stage_s + (uint32_t)(((gi & 1) * NSS + lane) * kSlot), (d ? pnb1 : pnb0) + (uint32_t)off,
+                 (uint32_t)kSlot, bar);
+      }
+      return n;
+    };
+
+    int cur_q = -1;
+    int beg = 0, end = 0, n = 0, nbeg = 0, nend = 0, nn = 0;
+    if (nunits > 0) n = issue(0, g, beg, end);
+    for (int u = 0; u < nunits; ++u, ++g) {
+      if (u + 1 < nunits) nn = issue(u + 1, g + 1, nbeg, nend);
+      const int d = u & 1, lr = warp + KW * (u >> 1);
+      const int q = lr >= lr_switch ? 1 : 0;
+      if (q != cur_q) {
+        cur_q = q;
+        x.load(&bf.x[q][0][0][lane * 4]);
+      }
+      mbar_wait(&bars[g & 1], (g >> 1) & 1);
+      const uint32_t sl = stage_lane + (g & 1) * (NSS * kSlot);
+      const uint32_t cy = rc_s + (uint32_t)((d * kTmaCap + beg) * 8 + 4);        // &rc[d][beg].y
+      float4 S0 = zero4(), S1 = S0, Q0 = S0, Q1 = S0;
+      float4 v1 = zero4();                                    // lanes without chunk-1 columns never overwrite it
+#pragma unroll
+      for (int i = 0; i < NSS; ++i) {
+        if (i < n) {
+          const float c = lds1(cy + i * 8);
+          const float4 v0 = lds4(sl + i * kSlot);
+          if (ld1) v1 = lds4(sl + i * kSlot + 512);
+          fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+        }
+      }
+      if (end - beg > n) {                                    // long rows: staged edges beyond the stage, then the rest
+        const char* tb = (d ? pnb1 : pnb0) + lane * 16;
+        const int fast_end = min(end, kTmaCap);
+        for (int i = beg + n; i < fast_end; ++i) {
+          const int2 m = bf.rc[d][i];
+          const char* a0 = tb + (uint32_t)m.x;
+          const float4 v0 = ldg4(a0);
+          if (ld1) v1 = ldg4(a0 + 512);
+          const float c = __int_as_float(m.y);
+          fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+        }
+        const PnDir& dd = p.dir[d];
+        const int ebase = d ? eb1 : eb0;
+        for (int i = max(beg + n, kTmaCap); i < end; ++i) {
+          const int64_t e = (int64_t)ebase + i;
+          const float w = dd.w ? dd.w[e] : 1.0f;
+          const float c = w * (w * p.prior[dd.src[e]]);
+          const char* a0 = tb + (uint32_t)dd.rel[e] * (uint32_t)kPnRowBytes;
+          const float4 v0 = ldg4(a0);
+          if (ld1) v1 = ldg4(a0 + 512);
+          fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+        }
+      }
+      __nv_bfloat16* const hrow = hi_lane + (int64_t)lr * p.ld;
+      __nv_bfloat16* const lrow = lo_lane + (int64_t)lr * p.ld;
+      const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);
+      const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int seg = d * SEGP + j * 2 * SEGP;
+        emit4(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
+        emit4(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
+      }
+      beg = nbeg; end = nend; n = nn;
+    }
+    mbar_arrive(&s_empty[it & 1]);
+  }
+}
+
+template <int NI, int KW, int ROWS>
+int launch_tma2(const PnParams& p, cudaStream_t stream) {
+  auto kern = agg_abs_tma2_kernel<NI, 200, 208, KW, ROWS>;
+  const size_t buf = (sizeof(int2) * 2 * kTmaCap + sizeof(float) * 2 * NI * 2 * kPnCols + 4 * 2 * (ROWS + 4) + 16 + 15) / 16 * 16;
+  const size_t smem = 2 * buf + (size_t)KW * 2 * kStageSlots * 200 * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+  const unsigned tiles = (unsigned)ceil_div(p.Nt, ROWS);
+  const unsigned pgrid = std::min<unsigned>(tiles, 2u * (unsigned)sm_count());
+  kern<<<pgrid, (KW + 1) * 32, smem, stream>>>(p, (int)tiles);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-gather kernel, third version (gr_set_option("agg_abs_ws", 32)): tile::gather4.
+//
+// scripts/micro/gather4_test.cu (profiles/r2_gather4_test.txt): `cp.async.bulk.tensor.2d ... tile::gather4` with a
+// {D columns, 1 row} box fetches FOUR table rows, given by four row coordinates, into 4 x 800 contiguous bytes; a row
+// coordinate beyond the tensor is zero-filled without a memory read and still counts its bytes on the mbarrier.  16
+// warps/SM issuing two of them per 8 edges gather at 16.5 TB/s -- with a quarter of the copy instructions of the
+// per-row bulk copies (each costs ~8-12 issue slots: UBLKCP / UTMALDG take uniform registers, ptxas walks the lanes).
+// Structure: one CTA per SM, 14 consumer warps + the staging warp; every consumer owns two stages of 8 slots (two
+// gather4 groups) and prefetches exactly one (row, direction) unit ahead, also across the tile boundary (non-blocking
+// peek at the next staged tile).  The accumulation loop is a real loop over the unit's edges (ptxas predicates an
+// unrolled `if (i < n)` chain: all 6 bodies issued for 4 edges on average -- measured, 340 instructions per unit).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kG4Slots = 8;                 // slots per stage = two gather4 groups
+constexpr int kOobRow = 0x3fffffff;         // row coordinate outside any table: zero fill, no memory traffic
+
+typedef CUresult (*AggEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool make_table_tmap(CUtensorMap* m, const float* pn, int64_t rows, int cols) {
+  static AggEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess &&
+        r == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<AggEncodeTiledFn>(q);
+  }
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)kPnCols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kPnRowBytes};
+  cuuint32_t box[2] = {(cuuint32_t)cols, 1u};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pn), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int r0, int r1, int r2,
+                                            int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(0), "r"(r0), "r"(r1),
+      "r"(r2), "r"(r3)
+      : "memory");
+}
+
+template <int NI, int ROWS>
+struct alignas(16) G4Buf {
+  int2 rc[2][kTmaCap];               // {relation row index, coefficient}
+  float x[2][NI][2][kPnCols];
+  int32_t rowptr[2][ROWS + 4];
+  int32_t tile;
+  int32_t nrows;
+  int32_t pad_[2];
+};
+
+template <int NI, int DT, int SEGP, int KW, int RPW>
+__global__ void __launch_bounds__((KW + 1) * 32, 1)
+agg_abs_tma3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                    const PnParams p, int ntiles) {
+  static_assert(DT % 4 == 0 && DT > 128 && DT <= kPnCols, "two column chunks of 128");
+  constexpr int ROWS = KW * RPW;
+  constexpr int NSS = kG4Slots;
+  constexpr int kSlot = DT * 4;
+  using Buf = G4Buf<NI, ROWS>;
+  extern __shared__ __align__(128) unsigned char ws_smem_raw[];
+  unsigned char* const ring_all = ws_smem_raw + ((128u - (smem_u32(ws_smem_raw) & 127u)) & 127u);
+  Buf* bufs = reinterpret_cast<Buf*>(ring_all + (size_t)KW * 2 * NSS * kSlot);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  __shared__ __align__(8) uint64_t s_bar[KW][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], KW * 32); mbar_init(&s_empty[1], KW * 32);
+    for (int w = 0; w < KW; ++w) { mbar_init(&s_bar[w][0], 1); mbar_init(&s_bar[w][1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == KW) {
+    // =============================== staging warp ===============================
+    for (int it = 0;; ++it) {
+      Buf& bf = bufs[it & 1];
+      if (it >= 2) mbar_wait(&s_empty[it & 1], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(p.tile_counter, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[it & 1]);
+        break;
+      }
+      if (lane == 0) bf.nrows = (int)min((int64_t)ROWS, p.Nt - (int64_t)tile * ROWS);
+      produce_tile_rows<NI, DT, ROWS, kTmaCap, true>(bf, p, tile, lane);
+      __syncwarp();
+      mbar_arrive(&s_full[it & 1]);
+    }
+    return;
+  }
+
+  // =============================== consumer warps ===============================
+  const bool ld1 = 128 + lane * 4 < DT;
+  const bool wr1 = 128 + lane * 4 < SEGP;
+  const char* const pnb0 = reinterpret_cast<const char*>(p.dir[0].pn) + lane * 16;
+  const char* const pnb1 = reinterpret_cast<const char*>(p.dir[1].pn) + lane * 16;
+  const uint32_t stage_s = smem_u32(ring_all) + (uint32_t)warp * 2u * NSS * kSlot;
+  const uint32_t stage_lane = stage_s + lane * 16;
+  uint64_t* const bars = s_bar[warp];
+  LaneIns<NI> x;
+  uint32_t g = 0;                     // units issued so far minus the one in flight: unit g lives in stage g & 1
+  int beg = 0, end = 0, n = 0;        // the unit whose copies are in flight / about to be consumed
+  bool pre = false;                   // unit 0 of the current tile was issued while finishing the previous tile
+
+  // issue the gather of unit u of the tile staged in b into stage gi & 1
+  auto issue = [&](const Buf& b, int u, uint32_t gi, int& ubeg, int& uend) -> int {
+    const int d = u & 1, lr = warp + KW * (u >> 1);
+    const int ebase = b.rowptr[d][0];
+    ubeg = b.rowptr[d][lr] - ebase;
+    uend = b.rowptr[d][lr + 1] - ebase;
+    const int un = max(0, min(min(uend, kTmaCap) - ubeg, NSS));
+    const int ng = (un + 3) >> 2;
+    uint64_t* const bar = &bars[gi & 1];
+    if (lane == 0) {
+      if (ng > 0) mbar_expect_tx(bar, (uint32_t)(ng * 4 * kSlot));
+      else mbar_arrive1(bar);
+    }
+    if (lane < ng) {
+      const int2* e = &b.rc[d][ubeg + 4 * lane];
+      const int left = un - 4 * lane;                         // >= 1
+      const int r0 = e[0].x;
+      const int r1 = left > 1 ? e[1].x : kOobRow;
+      const int r2 = left > 2 ? e[2].x : kOobRow;
+      const int r3 = left > 3 ? e[3].x : kOobRow;
+      tma_gather4(stage_s + (uint32_t)(((gi & 1) * NSS + 4 * lane) * kSlot), d ? &map1 : &map0, bar, r0, r1, r2, r3);
+    }
+    return un;
+  };
+
+  for (int it = 0;; ++it) {
+    Buf& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int64_t r0 = (int64_t)tile * ROWS;
+    const int nrows = bf.nrows;
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    __nv_bfloat16* const hi_lane = p.out_hi + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* const lo_lane = p.out_lo + r0 * p.ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    const int nunits = warp < nrows ? 2 * ((nrows - warp + KW - 1) / KW) : 0;
+    const uint32_t rc_s = smem_u32(&bf.rc[0][0]);
+    int cur_q = -1;
+    if (nunits > 0 && !pre) n = issue(bf, 0, g, beg, end);
+    pre = false;
+    for (int u = 0; u < nunits; ++u, ++g) {
+      int nbeg = 0, nend = 0, nn = 0;
+      if (u + 1 < nunits) {
+        nn = issue(bf, u + 1, g + 1, nbeg, nend);
+      } else if (mbar_test(&s_full[(it + 1) & 1], ((it + 1) >> 1) & 1)) {   // last unit: peek at the next staged tile
+        const Buf& nb = bufs[(it + 1) & 1];
+        if (nb.tile >= 0 && warp < nb.nrows) {
+          nn = issue(nb, 0, g + 1, nbeg, nend);
+          pre = true;
+        }
+      }
+      const int d = u & 1, lr = warp + KW * (u >> 1);
+      const int q = lr >= lr_switch ? 1 : 0;
+      if (q != cur_q) {
+        cur_q = q;
+        x.load(&bf.x[q][0][0][lane * 4]);
+      }
+      mbar_wait(&bars[g & 1], (g >> 1) & 1);
+      uint32_t sl = stage_lane + (g & 1) * (NSS * kSlot);
+      uint32_t cy = rc_s + (uint32_t)((d * kTmaCap + beg) * 8 + 4);        // &rc[d][beg].y
+      float4 S0 = zero4(), S1 = S0, Q0 = S0, Q1 = S0;
+      float4 v1 = zero4();                                    // lanes without chunk-1 columns never overwrite it
+#pragma unroll 1
+      for (int i = 0; i < n; ++i, sl += kSlot, cy += 8) {
+        const float c = lds1(cy);
+        const float4 v0 = lds4(sl);
+        if (ld1) v1 = lds4(sl + 512);
+        fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+      }
+      if (end - beg > n) {                                    // long rows: staged edges beyond the stage, then the rest
+        const char* tb = d ? pnb1 : pnb0;
+        const int fast_end = min(end, kTmaCap);
+        for (int i = beg + n; i < fast_end; ++i) {
+          const int2 m = bf.rc[d][i];
+          const char* a0 = tb + (size_t)(uint32_t)m.x * kPnRowBytes;
+          const float4 v0 = ldg4(a0);
+          if (ld1) v1 = ldg4(a0 + 512);
+          const float c = __int_as_float(m.y);
+          fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+        }
+        const PnDir& dd = p.dir[d];
+        const int ebase = bf.rowptr[d][0];
+        for (int i = max(beg + n, kTmaCap); i < end; ++i) {
+          const int64_t e = (int64_t)ebase + i;
+          const float w = dd.w ? dd.w[e] : 1.0f;
+          const float c = w * (w * p.prior[dd.src[e]]);
+          const char* a0 = tb + (size_t)(uint32_t)dd.rel[e] * kPnRowBytes;
+          const float4 v0 = ldg4(a0);
+          if (ld1) v1 = ldg4(a0 + 512);
+          fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+        }
+      }
+      __nv_bfloat16* const hrow = hi_lane + (int64_t)lr * p.ld;
+      __nv_bfloat16* const lrow = lo_lane + (int64_t)lr * p.ld;
+      const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);
+      const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int seg = d * SEGP + j * 2 * SEGP;
+        emit4(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
+        emit4(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
+      }
+      beg = nbeg; end = nend; n = nn;
+    }
+    mbar_arrive(&s_empty[it & 1]);
+  }
+}
+
+template <int NI, int KW, int RPW>
+int launch_tma3(const PnParams& p, cudaStream_t stream) {
+  auto kern = agg_abs_tma3_kernel<NI, 200, 208, KW, RPW>;
+  const size_t smem = 128 + (size_t)KW * 2 * kG4Slots * 200 * 4 + 2 * sizeof(G4Buf<NI, KW * RPW>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  CUtensorMap m0, m1;
+  if (!make_table_tmap(&m0, p.dir[0].pn, p.table_rows, 200) || !make_table_tmap(&m1, p.dir[1].pn, p.table_rows, 200)) {
+    set_error("gr_aggregate_dual_abs: cuTensorMapEncodeTiled failed for the padded relation table");
+    return GR_ERR_CUDA;
+  }
+  GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+  const unsigned tiles = (unsigned)ceil_div(p.Nt, KW * RPW);
+  const unsigned pgrid = std::min<unsigned>(tiles, (unsigned)sm_count());
+  kern<<<pgrid, (KW + 1) * 32, smem, stream>>>(m0, m1, p, (int)tiles);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// gather4 kernel, refined (gr_set_option("agg_abs_ws", 33)).  What the profile of agg_abs_tma3_kernel said
+// (profiles/README.md): 308 instructions per unit -- 75 to issue the prefetch (row pointers, clamping, address
+// arithmetic, the coordinate loads), 30 around the mbarrier wait, 20 CS2R of accumulator zeroing, 17 per edge, 94 in
+// the epilogue -- and 15 % of the stall samples on the tile hand-over: one staging warp cannot feed 14 consumers.
+// Here:
+//   * two staging warps (even / odd tiles; a shared-memory turn counter keeps their tile grabs in hand-over order);
+//   * the staging warp leaves, per (row, direction) unit, a descriptor {first staged edge, #stage edges, long-row flag}
+//     and the two ready-made gather4 coordinate quads (out-of-table coordinates where the unit has fewer edges), so a
+//     consumer's prefetch is one LDS + one LDS.128 + the copy;
+//   * the direction loop is unrolled inside the row loop: descriptor / quad / tensor-map addresses are immediates;
+//   * accumulators start from the first edge's products (no zeroing), two edges per loop trip.
+// ---------------------------------------------------------------------------------------------------------
+template <int NI, int ROWS>
+struct alignas(16) G5Buf {
+  int4 quad[2][ROWS][2];             // gather4 row coordinates of the unit's stage edges 0-3 / 4-7
+  int2 rc[2][kTmaCap];               // {relation row index, coefficient}
+  float x[2][NI][2][kPnCols];
+  int32_t rowptr[2][ROWS + 4];
+  uint32_t ud[2][ROWS];              // first staged edge | #stage edges << 16 | (unit has more edges than that) << 31
+  int32_t tile;
+  int32_t nrows;
+  int32_t pad_[2];
+};
+
+template <int NI, int DT, int SEGP, int KW, int RPW>
+__global__ void __launch_bounds__((KW + 2) * 32, 1)
+agg_abs_g4_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                  const PnParams p, int ntiles) {
+  static_assert(DT % 4 == 0 && DT > 128 && DT <= kPnCols, "two column chunks of 128");
+  constexpr int ROWS = KW * RPW;
+  constexpr int NSS = kG4Slots;
+  constexpr int kSlot = DT * 4;
+  using Buf = G5Buf<NI, ROWS>;
+  extern __shared__ __align__(128) unsigned char ws_smem_raw[];
+  // gather4 destinations must be 128-byte aligned; the dynamic segment only follows the static one at 16 bytes
+  unsigned char* const ring_all = ws_smem_raw + ((128u - (smem_u32(ws_smem_raw) & 127u)) & 127u);
+  Buf* bufs = reinterpret_cast<Buf*>(ring_all + (size_t)KW * 2 * NSS * kSlot);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  __shared__ __align__(8) uint64_t s_bar[KW][2];
+  __shared__ volatile int s_turn;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], KW * 32); mbar_init(&s_empty[1], KW * 32);
+    for (int w = 0; w < KW; ++w) { mbar_init(&s_bar[w][0], 1); mbar_init(&s_bar[w][1], 1); }
+    s_turn = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= KW) {
+    // =============================== staging warps: warp KW -> even iterations, KW + 1 -> odd ===============
+    const int par = warp - KW;
+    Buf& bf = bufs[par];
+    for (int it = par;; it += 2) {
+      if (it >= 2) mbar_wait(&s_empty[par], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) {
+        while (s_turn != it) __nanosleep(20);                 // tiles are grabbed in hand-over order
+        tile = atomicAdd(p.tile_counter, 1);
+        __threadfence_block();
+        s_turn = it + 1;
+      }
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[par]);
+        break;
+      }
+      const int nrows = (int)min((int64_t)ROWS, p.Nt - (int64_t)tile * ROWS);
+      if (lane == 0) bf.nrows = nrows;
+      produce_tile_rows<NI, DT, ROWS, kTmaCap, true>(bf, p, tile, lane);
+      __syncwarp();
+      for (int un = lane; un < 2 * nrows; un += 32) {          // unit descriptors + gather4 coordinate quads
+        const int d = un >= nrows ? 1 : 0, lr = un - d * nrows;
+        const int ebase = bf.rowptr[d][0];
+        const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+        const int n = max(0, min(min(end, kTmaCap) - beg, NSS));
+        int r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = k < n ? bf.rc[d][beg + k].x : kOobRow;
+        bf.quad[d][lr][0] = make_int4(r[0], r[1], r[2], r[3]);
+        bf.quad[d][lr][1] = make_int4(r[4], r[5], r[6], r[7]);
+        bf.ud[d][lr] = (uint32_t)min(beg, kTmaCap) | ((uint32_t)n << 16) | (end - beg > n ? 0x80000000u : 0u);
+      }
+      __syncwarp();
+      mbar_arrive(&s_full[par]);
+    }
+    return;
+  }
+
+  // =============================== consumer warps ===============================
+  const bool ld1 = 128 + lane * 4 < DT;
+  const bool wr1 = 128 + lane * 4 < SEGP;
+  const uint32_t stage_s = smem_u32(ring_all) + (uint32_t)warp * 2u * NSS * kSlot;   // stage 0: direction 0, stage 1: 1
+  const uint32_t stage_lane = stage_s + lane * 16;
+  uint64_t* const bars = s_bar[warp];
+  LaneIns<NI> x;
+  uint32_t ph = 0;                    // rows consumed so far by this warp: both stage barriers are at phase parity ph & 1
+  uint32_t desc0 = 0;                 // descriptor of the direction-0 unit in flight
+  bool pre = false;
+
+  // prefetch unit (lr, D) of the tile staged in b into stage D; returns its descriptor
+  auto issue = [&](const Buf& b, int lr, auto dir) -> uint32_t {
+    constexpr int D_ = decltype(dir)::value;
+    const uint32_t desc = b.ud[D_][lr];
+    const int ng = (int)(((desc >> 16) & 0xffu) + 3u) >> 2;
+    uint64_t* const bar = &bars[D_];
+    if (lane == 0) {
+      if (ng > 0) mbar_expect_tx(bar, (uint32_t)(ng * 4 * kSlot));
+      else mbar_arrive1(bar);
+    }
+    if (lane < ng) {
+      const int4 q = b.quad[D_][lr][lane];
+      tma_gather4(stage_s + (uint32_t)((D_ * NSS + 4 * lane) * kSlot), D_ ? &map1 : &map0, bar, q.x, q.y, q.z, q.w);
+    }
+    return desc;
+  };
+
+  // accumulate + emit one unit from its stage
+  auto consume = [&](Buf& bf, int lr, auto dir, uint32_t desc, __nv_bfloat16* hrow, __nv_bfloat16* lrow) {
+    constexpr int D_ = decltype(dir)::value;
+    const int beg = (int)(desc & 0xffffu), n = (int)((desc >> 16) & 0xffu);
+    uint32_t sl = stage_lane + D_ * (NSS * kSlot);
+    uint32_t cy = smem_u32(&bf.rc[D_][0]) + (uint32_t)(beg * 8 + 4);
+    float4 S0, S1, Q0, Q1;
+    float4 v1 = zero4();                                      // lanes without chunk-1 columns never overwrite it
+    if (n > 0) {
+      const float c = lds1(cy);
+      const float4 v0 = lds4(sl);
+      if (ld1) v1 = lds4(sl + 512);
+      S0 = zero4(); S1 = S0; Q0 = S0; Q1 = S0;
+      fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+      int i = 1;
+#pragma unroll 1
+      for (; i + 1 < n; i += 2) {
+        sl += 2 * kSlot; cy += 16;
+        const float ca = lds1(cy - 8), cb = lds1(cy);
+        const float4 a0 = lds4(sl - kSlot), b0 = lds4(sl);
+        float4 a1 = v1, b1 = v1;
+        if (ld1) { a1 = lds4(sl - kSlot + 512); b1 = lds4(sl + 512); }
+        fma4(S0, ca, a0); fma4_abs(Q0, ca, a0); fma4(S1, ca, a1); fma4_abs(Q1, ca, a1);
+        fma4(S0, cb, b0); fma4_abs(Q0, cb, b0); fma4(S1, cb, b1); fma4_abs(Q1, cb, b1);
+      }
+      if (i < n) {
+        sl += kSlot; cy += 8;
+        const float cc = lds1(cy);
+        const float4 c0 = lds4(sl);
+        if (ld1) v1 = lds4(sl + 512);
+        fma4(S0, cc, c0); fma4_abs(Q0, cc, c0); fma4(S1, cc, v1); fma4_abs(Q1, cc, v1);
+      }
+    } else {
+      S0 = zero4(); S1 = S0; Q0 = S0; Q1 = S0;
+    }
+    if (desc >> 31) {                                         // long rows: staged edges beyond the stage, then the rest
+      const char* tb = reinterpret_cast<const char*>(p.dir[D_].pn) + lane * 16;
+      const int ebase = bf.rowptr[D_][0];
+      const int rb = bf.rowptr[D_][lr] - ebase, end = bf.rowptr[D_][lr + 1] - ebase;
+      const int fast_end = min(end, kTmaCap);
+      for (int i = rb + n; i < fast_end; ++i) {
+        const int2 m = bf.rc[D_][i];
+        const char* a0 = tb + (size_t)(uint32_t)m.x * kPnRowBytes;
+        const float4 v0 = ldg4(a0);
+        if (ld1) v1 = ldg4(a0 + 512);
+        const float c = __int_as_float(m.y);
+        fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+      }
+      const PnDir& dd = p.dir[D_];
+      for (int i = max(rb + n, kTmaCap); i < end; ++i) {
+        const int64_t e = (int64_t)ebase + i;
+        const float w = dd.w ? dd.w[e] : 1.0f;
+        const float c = w * (w * p.prior[dd.src[e]]);
+        const char* a0 = tb + (size_t)(uint32_t)dd.rel[e] * kPnRowBytes;
+        const float4 v0 = ldg4(a0);
+        if (ld1) v1 = ldg4(a0 + 512);
+        fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+      }
+    }
+    const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);
+    const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int seg = D_ * SEGP + j * 2 * SEGP;
+      emit4(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
+      emit4(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
+    }
+  };
+  using Dir0 = std::integral_constant<int, 0>;
+  using Dir1 = std::integral_constant<int, 1>;
+
+  for (int it = 0;; ++it) {
+    Buf& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int64_t r0 = (int64_t)tile * ROWS;
+    const int nrows = bf.nrows;
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    const int64_t ld = p.ld;
+    __nv_bfloat16* hrow = p.out_hi + (r0 + warp) * ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* lrow = p.out_lo + (r0 + warp) * ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    int cur_q = -1;
+    if (warp < nrows && !pre) desc0 = issue(bf, warp, Dir0{});
+    pre = false;
+    for (int lr = warp; lr < nrows; lr += KW, ++ph, hrow += KW * ld, lrow += KW * ld) {
+      const uint32_t desc1 = issue(bf, lr, Dir1{});           // direction 1 of this row flies while direction 0 is consumed
+      const int q = lr >= lr_switch ? 1 : 0;
+      if (q != cur_q) {
+        cur_q = q;
+        x.load(&bf.x[q][0][0][lane * 4]);
+      }
+      mbar_wait(&bars[0], ph & 1);
+      consume(bf, lr, Dir0{}, desc0, hrow, lrow);
+      if (lr + KW < nrows) {                                  // direction 0 of the next row
+        desc0 = issue(bf, lr + KW, Dir0{});
+      } else if (mbar_test(&s_full[(it + 1) & 1], ((it + 1) >> 1) & 1)) {     // ... or of the next staged tile
+        const Buf& nb = bufs[(it + 1) & 1];
+        if (nb.tile >= 0 && warp < nb.nrows) {
+          desc0 = issue(nb, warp, Dir0{});
+          pre = true;
+        }
+      }
+      mbar_wait(&bars[1], ph & 1);
+      consume(bf, lr, Dir1{}, desc1, hrow, lrow);
+    }
+    mbar_arrive(&s_empty[it & 1]);
+  }
+}
+
+template <int NI, int KW, int RPW>
+int launch_g4(const PnParams& p, cudaStream_t stream) {
+  auto kern = agg_abs_g4_kernel<NI, 200, 208, KW, RPW>;
+  const size_t smem = 128 + (size_t)KW * 2 * kG4Slots * 200 * 4 + 2 * sizeof(G5Buf<NI, KW * RPW>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  CUtensorMap m0, m1;
+  if (!make_table_tmap(&m0, p.dir[0].pn, p.table_rows, 200) || !make_table_tmap(&m1, p.dir[1].pn, p.table_rows, 200)) {
+    set_error("gr_aggregate_dual_abs: cuTensorMapEncodeTiled failed for the padded relation table");
+    return GR_ERR_CUDA;
+  }
+  GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+  const unsigned tiles = (unsigned)ceil_div(p.Nt, KW * RPW);
+  const unsigned pgrid = std::min<unsigned>(tiles, (unsigned)sm_count());
+  kern<<<pgrid, (KW + 2) * 32, smem, stream>>>(m0, m1, p, (int)tiles);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// gather4 kernel with a deeper prefetch (gr_set_option("agg_abs_ws", 34)).
+// Three gather kernels with very different instruction counts (tma2 340, tma3 308, g4 303 per unit) all ran 157.5 us:
+// 1730 units per SM / 14 warps x 1.27 us.  With the copies of unit k + 1 issued when unit k starts, a unit cannot
+// take less than the latency of a TMA gather (issue -> bytes landed -> mbarrier flip -> waiter resumes), ~1.3 us here,
+// three times the LDG round trip.  So the per-warp ring is cut into FOUR groups of four slots (one gather4 each): a
+// unit takes one or two groups (its first <= 8 staged edges), its mbarrier is the one of its first group, and a flat
+// prefetch cursor keeps issuing ahead (across the tile boundary) while groups are free: 2-3 units in flight.
+// ---------------------------------------------------------------------------------------------------------
+template <int NI, int DT, int SEGP, int KW, int RPW>
+__global__ void __launch_bounds__((KW + 2) * 32, 1)
+agg_abs_g5_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                  const PnParams p, int ntiles) {
+  static_assert(DT % 4 == 0 && DT > 128 && DT <= kPnCols, "two column chunks of 128");
+  constexpr int ROWS = KW * RPW;
+  constexpr int kSlot = DT * 4;
+  constexpr int kGroup = 4 * kSlot;            // bytes of one gather4 group
+  using Buf = G5Buf<NI, ROWS>;
+  extern __shared__ __align__(128) unsigned char ws_smem_raw[];
+  unsigned char* const ring_all = ws_smem_raw + ((128u - (smem_u32(ws_smem_raw) & 127u)) & 127u);
+  Buf* bufs = reinterpret_cast<Buf*>(ring_all + (size_t)KW * 4 * kGroup);
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  __shared__ __align__(8) uint64_t s_bar[KW][4];
+  __shared__ volatile int s_turn;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 32); mbar_init(&s_full[1], 32);
+    mbar_init(&s_empty[0], KW * 32); mbar_init(&s_empty[1], KW * 32);
+    for (int w = 0; w < KW; ++w)
+      for (int b = 0; b < 4; ++b) mbar_init(&s_bar[w][b], 1);
+    s_turn = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= KW) {
+    // =============================== staging warps: warp KW -> even iterations, KW + 1 -> odd ===============
+    const int par = warp - KW;
+    Buf& bf = bufs[par];
+    for (int it = par;; it += 2) {
+      if (it >= 2) mbar_wait(&s_empty[par], ((it >> 1) - 1) & 1);
+      int tile = 0;
+      if (lane == 0) {
+        while (s_turn != it) __nanosleep(20);                 // tiles are grabbed in hand-over order
+        tile = atomicAdd(p.tile_counter, 1);
+        __threadfence_block();
+        s_turn = it + 1;
+      }
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= ntiles) {
+        if (lane == 0) bf.tile = -1;
+        __syncwarp();
+        mbar_arrive(&s_full[par]);
+        break;
+      }
+      const int nrows = (int)min((int64_t)ROWS, p.Nt - (int64_t)tile * ROWS);
+      if (lane == 0) bf.nrows = nrows;
+      produce_tile_rows<NI, DT, ROWS, kTmaCap, true>(bf, p, tile, lane);
+      __syncwarp();
+      for (int un = lane; un < 2 * nrows; un += 32) {          // unit descriptors + gather4 coordinate quads
+        const int d = un >= nrows ? 1 : 0, lr = un - d * nrows;
+        const int ebase = bf.rowptr[d][0];
+        const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+        const int n = max(0, min(min(end, kTmaCap) - beg, 8));
+        int r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = k < n ? bf.rc[d][beg + k].x : kOobRow;
+        bf.quad[d][lr][0] = make_int4(r[0], r[1], r[2], r[3]);
+        bf.quad[d][lr][1] = make_int4(r[4], r[5], r[6], r[7]);
+        bf.ud[d][lr] = (uint32_t)min(beg, kTmaCap) | ((uint32_t)n << 16) | (end - beg > n ? 0x80000000u : 0u);
+      }
+      __syncwarp();
+      mbar_arrive(&s_full[par]);
+    }
+    return;
+  }
+
+  // =============================== consumer warps ===============================
+  const bool ld1 = 128 + lane * 4 < DT;
+  const bool wr1 = 128 + lane * 4 < SEGP;
+  const uint32_t ring_s = smem_u32(ring_all) + (uint32_t)warp * 4u * kGroup;   // this warp's four groups
+  const uint32_t ring_lane = ring_s + lane * 16;
+  uint64_t* const bars = s_bar[warp];
+  LaneIns<NI> x;
+  // ring state (all warp-uniform)
+  int gh = 0, gc = 0, gfree = 4;      // next group to fill / group of the unit being consumed / free groups
+  uint32_t parbits = 0;               // phase parity of the four group barriers
+  // prefetch cursor: next unit to issue = (tile iteration pit, row plr, direction pd); pnrows = rows of that tile
+  int pit = -1, plr = 0, pd = 0, pnrows = 0;
+  bool pend = false;                  // the cursor has seen the end marker
+
+  for (int it = 0;; ++it) {
+    Buf& bf = bufs[it & 1];
+    mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+    const int tile = bf.tile;
+    if (tile < 0) break;
+    const int64_t r0 = (int64_t)tile * ROWS;
+    const int nrows = bf.nrows;
+    const int b0 = (int)(r0 / N);
+    const int lr_switch = N - (int)(r0 - (int64_t)b0 * N);
+    const int64_t ld = p.ld;
+    __nv_bfloat16* hrow = p.out_hi + (r0 + warp) * ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    __nv_bfloat16* lrow = p.out_lo + (r0 + warp) * ld + p.out_col0 + lane * 4 + (int64_t)p.j0 * 2 * SEGP;
+    if (pit < it) { pit = it; plr = warp; pd = 0; pnrows = nrows; }
+    int cur_q = -1;
+    for (int lr = warp; lr < nrows; lr += KW, hrow += KW * ld, lrow += KW * ld) {
+      const int q = lr >= lr_switch ? 1 : 0;
+      if (q != cur_q) {
+        cur_q = q;
+        x.load(&bf.x[q][0][0][lane * 4]);
+      }
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        // ---------------- keep the ring full ----------------
+        for (;;) {
+          if (plr >= pnrows) {                                // cursor at the end of its tile
+            if (pend || pit > it) break;                      // never two tiles ahead (that buffer is this one)
+            if (!mbar_test(&s_full[(it + 1) & 1], ((it + 1) >> 1) & 1)) break;
+            const Buf& nb = bufs[(it + 1) & 1];
+            pit = it + 1; plr = warp; pd = 0;
+            if (nb.tile < 0) { pend = true; pnrows = 0; break; }
+            pnrows = nb.nrows;
+            continue;
+          }
+          const Buf& pb = bufs[pit & 1];
+          const uint32_t pdesc = pb.ud[pd][plr];
+          const int ng = (int)(((pdesc >> 16) & 0xffu) + 3u) >> 2;
+          if (ng > gfree) break;
+          if (ng > 0) {
+            uint64_t* const bar = &bars[gh];
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)(ng * kGroup));
+            if (lane < ng) {
+              const int4 qd = pb.quad[pd][plr][lane];
+              tma_gather4(ring_s + (uint32_t)(((gh + lane) & 3) * kGroup), pd ? &map1 : &map0, bar, qd.x, qd.y, qd.z, qd.w);
+            }
+            gh = (gh + ng) & 3;
+            gfree -= ng;
+          }
+          pd ^= 1;
+          if (pd == 0) plr += KW;
+        }
+        // ---------------- consume unit (lr, d) ----------------
+        const uint32_t desc = bf.ud[d][lr];
+        const int beg = (int)(desc & 0xffffu), n = (int)((desc >> 16) & 0xffu);
+        float4 S0 = zero4(), S1 = S0, Q0 = S0, Q1 = S0;
+        float4 v1 = zero4();                                  // lanes without chunk-1 columns never overwrite it
+        if (n > 0) {
+          mbar_wait(&bars[gc], (parbits >> gc) & 1u);
+          parbits ^= 1u << gc;
+          uint32_t cy = smem_u32(&bf.rc[d][0]) + (uint32_t)(beg * 8 + 4);
+          uint32_t sl = ring_lane + (uint32_t)gc * kGroup;
+          const int n0 = min(n, 4);
+#pragma unroll 1
+          for (int i = 0; i < n0; ++i, sl += kSlot, cy += 8) {
+            const float c = lds1(cy);
+            const float4 v0 = lds4(sl);
+            if (ld1) v1 = lds4(sl + 512);
+            fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+          }
+          if (n > 4) {
+            sl = ring_lane + (uint32_t)((gc + 1) & 3) * kGroup;
+#pragma unroll 1
+            for (int i = 4; i < n; ++i, sl += kSlot, cy += 8) {
+              const float c = lds1(cy);
+              const float4 v0 = lds4(sl);
+              if (ld1) v1 = lds4(sl + 512);
+              fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+            }
+          }
+          const int ngc = (n + 3) >> 2;
+          gc = (gc + ngc) & 3;
+          gfree += ngc;
+        }
+        if (desc >> 31) {                                     // long rows: staged edges beyond the ring, then the rest
+          const char* tb = reinterpret_cast<const char*>(p.dir[d].pn) + lane * 16;
+          const int ebase = bf.rowptr[d][0];
+          const int rb = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
+          const int fast_end = min(end, kTmaCap);
+          for (int i = rb + n; i < fast_end; ++i) {
+            const int2 m = bf.rc[d][i];
+            const char* a0 = tb + (size_t)(uint32_t)m.x * kPnRowBytes;
+            const float4 v0 = ldg4(a0);
+            if (ld1) v1 = ldg4(a0 + 512);
+            const float c = __int_as_float(m.y);
+            fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+          }
+          const PnDir& dd = p.dir[d];
+          for (int i = max(rb + n, kTmaCap); i < end; ++i) {
+            const int64_t e = (int64_t)ebase + i;
+            const float w = dd.w ? dd.w[e] : 1.0f;
+            const float c = w * (w * p.prior[dd.src[e]]);
+            const char* a0 = tb + (size_t)(uint32_t)dd.rel[e] * kPnRowBytes;
+            const float4 v0 = ldg4(a0);
+            if (ld1) v1 = ldg4(a0 + 512);
+            fma4(S0, c, v0); fma4_abs(Q0, c, v0); fma4(S1, c, v1); fma4_abs(Q1, c, v1);
+          }
+        }
+        const float4 U0 = addsub4(Q0, S0, 1.f), V0 = addsub4(Q0, S0, -1.f);
+        const float4 U1 = addsub4(Q1, S1, 1.f), V1 = addsub4(Q1, S1, -1.f);
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int seg = d * SEGP + j * 2 * SEGP;
+          emit4(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
+          emit4(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
+        }
+      }
+    }
+    mbar_arrive(&s_empty[it & 1]);
+  }
+}
+
+template <int NI, int KW, int RPW>
+int launch_g5(const PnParams& p, cudaStream_t stream) {
+  auto kern = agg_abs_g5_kernel<NI, 200, 208, KW, RPW>;
+  const size_t smem = 128 + (size_t)KW * 16 * 200 * 4 + 2 * sizeof(G5Buf<NI, KW * RPW>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  CUtensorMap m0, m1;
+  if (!make_table_tmap(&m0, p.dir[0].pn, p.table_rows, 200) || !make_table_tmap(&m1, p.dir[1].pn, p.table_rows, 200)) {
+    set_error("gr_aggregate_dual_abs: cuTensorMapEncodeTiled failed for the padded relation table");
+    return GR_ERR_CUDA;
+  }
+  GR_CHECK_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream));
+  const unsigned tiles = (unsigned)ceil_div(p.Nt, KW * RPW);
+  const unsigned pgrid = std::min<unsigned>(tiles, (unsigned)sm_count());
+  kern<<<pgrid, (KW + 2) * 32, smem, stream>>>(m0, m1, p, (int)tiles);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
 // table [rows, D] fp32 (row stride ldt) -> zero-padded [rows][256]
 __global__ void pad_table_kernel(const float* __restrict__ table, int64_t ldt, int64_t rows, int D,
                                  float* __restrict__ out) {
@@ -1485,6 +2435,12 @@ int launch_pn(const PnParams& p, cudaStream_t stream) {
   }
   if constexpr (NI == 2) {
     if (p.tile_counter && g_opt_agg_abs_ws == 20) return launch_ring<2, 8, 96>(p, stream);
+    if (p.tile_counter && g_opt_agg_abs_ws == 30) return launch_tma2<2, 8, 64>(p, stream);
+    if (p.tile_counter && g_opt_agg_abs_ws == 32) return launch_tma3<2, 14, 4>(p, stream);
+    if (p.tile_counter && g_opt_agg_abs_ws == 33) return launch_g4<2, 14, 4>(p, stream);
+    if (p.tile_counter && g_opt_agg_abs_ws == 34) return launch_g5<2, 14, 4>(p, stream);
+    if (p.tile_counter && g_opt_agg_abs_ws == 35) return launch_g5<2, 14, 8>(p, stream);
+    if (p.tile_counter && g_opt_agg_abs_ws == 31) return launch_tma2<2, 8, 128>(p, stream);
     if (p.tile_counter && g_opt_agg_abs_ws >= 10) {
       switch (g_opt_agg_abs_ws) {
         case 10: return launch_wsg<2, 8, 64, 2>(p, stream);
@@ -1590,6 +2546,7 @@ extern "C" int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src
   p.ld = ld_planes; p.out_col0 = out_col0; p.Nt = (int64_t)B * N;
   p.B = B; p.N = N; p.I = I; p.tile_counter = tile_counter;
   p.hot_rel = g_opt_agg_hot_rel;
+  p.table_rows = g_opt_agg_table_rows;
   for (int j0 = 0; j0 < I; j0 += 4) {
     p.j0 = j0;
     const int ni = I - j0 < 4 ? I - j0 : 4;

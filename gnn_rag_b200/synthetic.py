@@ -170,3 +170,32 @@ CONFIGS = {
     "cfg4": dict(B=1024, N=2000, E=6000, D=200, T=3, K=3, I=2),
     "cfg5": dict(B=1, N=100_000, E=1_000_000, D=400, T=3, K=3, I=2),
 }
+
+
+def seeded_state_dict(shapes, seed=0, sharpen=None):
+    """Deterministic weights for a ``{name: shape}`` map, independent of module construction order and of torch's RNG:
+    every tensor comes from its own ``numpy.random.RandomState(crc32(name) + seed)``.  Embeddings ~ N(0, 1) (torch's
+    default), matrices ~ U(+-1/sqrt(fan_in)), vectors ~ U(+-0.05).  Lets the hot-shape goldens (tests/golden/
+    make_golden_hot.py, generated from the unmodified reference) store OUTPUTS only: the test rebuilds the same
+    weights.  ``sharpen = (e2e, rel, score)`` scales those weight groups like tests/golden/make_golden.py:sharpen."""
+    import zlib
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        rs = np.random.RandomState((zlib.crc32(name.encode()) + seed) % (2 ** 31))
+        if "embedding" in name:
+            w = rs.standard_normal(shape)
+        elif len(shape) >= 2:
+            w = rs.uniform(-1.0, 1.0, shape) / np.sqrt(shape[-1])
+        else:
+            w = rs.uniform(-0.05, 0.05, shape)
+        if sharpen is not None:
+            e2e, rel, score = sharpen
+            if "e2e_linear" in name and name.endswith("weight"):
+                w = w * e2e
+            if "rel_linear" in name and name.endswith("weight"):
+                w = w * rel
+            if name.endswith("reasoning.score_func.weight"):
+                w = w * score
+        out[name] = w.astype(np.float32)
+    return out

@@ -57,6 +57,31 @@ def _import_reference():
     return _state["mods"]
 
 
+def patch_transformers_offline(lm_config):
+    """Harness-side stand-in for the hub downloads of bert_encoder.py:31-60,72 (no network here): the tokenizer
+    becomes a stub that only knows its pad token id, the encoder is built from ``lm_config`` (a small BertConfig)
+    with random weights.  Reference files untouched."""
+    import torch
+    import transformers
+
+    class _Tok:
+        pad_token = "[PAD]"
+
+        def convert_tokens_to_ids(self, tok):
+            return 0
+
+    def tok_from_pretrained(name, *a, **k):
+        return _Tok()
+
+    def model_from_pretrained(name, *a, **k):
+        torch.manual_seed(1234)
+        return transformers.AutoModel.from_config(transformers.BertConfig(**lm_config))
+
+    import modules.question_encoding.bert_encoder as be
+    be.AutoTokenizer = type("AutoTokenizer", (), {"from_pretrained": staticmethod(tok_from_pretrained)})
+    be.AutoModel = type("AutoModel", (), {"from_pretrained": staticmethod(model_from_pretrained)})
+
+
 def data_folder():
     if "folder" not in _state:
         d = tempfile.mkdtemp(prefix="gr_ref_")

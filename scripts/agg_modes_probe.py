@@ -32,6 +32,7 @@ abytes = 2 * F * 8 + 2 * (B * N + 1) * 4 + B * N * 4 + 2 * (R + 1) * D * 4 + B *
 def run(mode, hot, planes):
     ops.set_option("agg_abs_ws", mode)
     ops.set_option("agg_hot_rel", hot)
+    ops.set_option("agg_table_rows", R + 1)
     ops.aggregate_dual_abs(g, prior, pf, pi, ins, planes, 208, 208)
 
 

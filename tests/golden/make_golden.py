@@ -89,13 +89,42 @@ CASES = {
                       batch=dict(seed=7, B=3, N=50, E=150, n_real="ragged", multi_seed=True)),
     "nsm_reason_kb": dict(model="NSM", D=20, kw=dict(num_step=2, reason_kb=True, normalized_gnn=True),
                           batch=dict(seed=8, B=4, N=40, E=120, n_real=30), sharpen=(1.5, 1.5, 50.0)),
+    # the configuration of the published checkpoints (gnn/README.md:19: --lm sbert --relation_word_emb True): language-model
+    # question encoder + relation-text relation features.  The hub model is replaced by a 1-layer BertConfig of the same
+    # width (384) in the harness (no network); token ids: pad = 0 (BERT), words 1..NUM_WORD.
+    "rearev_sbert_reltext": dict(model="ReaRev", D=24,
+                                 kw=dict(num_iter=2, num_ins=2, num_gnn=2, lm="sbert", relation_word_emb=True,
+                                         lm_config=dict(vocab_size=NUM_WORD + 2, hidden_size=384, num_hidden_layers=1,
+                                                        num_attention_heads=12, intermediate_size=32,
+                                                        max_position_embeddings=32, hidden_dropout_prob=0.0,
+                                                        attention_probs_dropout_prob=0.0)),
+                                 batch=dict(seed=9, B=3, N=48, E=160, n_real="ragged", multi_seed=True),
+                                 sharpen=(2.0, 2.0, 25.0)),
 }
+
+
+def bert_tokens(q_input, num_word):
+    """synthetic token ids (pad = num_word) -> BERT convention (pad = 0, words shifted by one)"""
+    return np.where(q_input == num_word, 0, q_input + 1).astype(np.int64)
+
+
+def make_rel_texts(seed, rows, L=5):
+    rs = np.random.RandomState(seed)
+    t = rs.randint(1, NUM_WORD + 1, size=(rows, L)).astype(np.int64)
+    for r in range(rows):
+        t[r, rs.randint(2, L + 1):] = 0                      # trailing pads
+    return t
 
 
 def main():
     mods = H._import_reference()
     for name, c in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         args = S.model_args(c["model"], entity_dim=c["D"], word_dim=24, **c["kw"])
+        lm = args.get("lm", "lstm") != "lstm"
+        if lm:
+            H.patch_transformers_offline(args["lm_config"])
         model = H.build_reference_model(args, NUM_ENTITY, NUM_REL, NUM_WORD, seed=0)
         if c.get("sharpen"):
             sharpen(model, *c["sharpen"])
@@ -105,6 +134,11 @@ def main():
                              Q=8, test=True, **bkw)
         if c.get("twins"):
             batch = add_twins(batch, N)
+        rel_texts = rel_texts_inv = None
+        if lm:
+            batch = batch[:3] + (bert_tokens(batch[3], NUM_WORD),) + batch[4:]
+            rel_texts, rel_texts_inv = make_rel_texts(31, NUM_REL + 1), make_rel_texts(32, NUM_REL + 1)
+            model.encode_rel_texts(rel_texts, rel_texts_inv)                   # gnn/train_model.py:62-64
         loss, pred, pred_dist = H.reference_forward(model, batch)
         retrieved = H.reference_rank(batch, pred_dist, NUM_ENTITY, args["eps"])
         blob = {"args_json": np.array(json.dumps(args))}
@@ -117,6 +151,8 @@ def main():
                      "batch/batch_ids": kb[3], "batch/fact_ids": kb[4],
                      "batch/weight_list": np.array(kb[5], dtype=np.float64),
                      "batch/weight_rel_list": np.array(kb[6], dtype=np.float64)})
+        if lm:
+            blob["batch/rel_texts"], blob["batch/rel_texts_inv"] = rel_texts, rel_texts_inv
         blob["out/loss"] = loss.numpy()
         blob["out/pred"] = pred.numpy()
         blob["out/pred_dist"] = pred_dist.numpy()

@@ -19,19 +19,28 @@ from golden_io import Golden  # noqa: E402
 from oracle import ref_harness as H  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "train")
-CASES = ["rearev_small", "rearev_norm", "rearev_posemb", "rearev_sharp_ties", "nsm_small", "nsm_reason_kb"]
+CASES = ["rearev_small", "rearev_norm", "rearev_posemb", "rearev_sharp_ties", "nsm_small", "nsm_reason_kb",
+         "rearev_sbert_reltext"]
 HIT_CASES = {"rearev_sharp_ties", "nsm_reason_kb", "rearev_small"}   # answers moved onto the top-1 node: h1 = 1, f1 > 0
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     for name in CASES:
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         g = Golden(name)
+        if g.args.get("lm", "lstm") != "lstm":
+            H._import_reference()
+            H.patch_transformers_offline(g.args["lm_config"])
         model = H.build_reference_model(g.args, g.num_entity, g.num_relation, g.num_word, seed=0)
         model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in g.sd.items()}, strict=True)
         model.eval()
-        for p in model.parameters():
-            p.requires_grad_(True)
+        if g.rel_texts is not None:
+            model.encode_rel_texts(g.rel_texts, g.rel_texts_inv)
+        for k, p in model.named_parameters():
+            if "node_encoder" not in k:                  # the language model stays frozen (lm_frozen = 1)
+                p.requires_grad_(True)
         batch = list(g.batch[:7])
         if name in HIT_CASES:      # random-init models never hit: make the forward golden's top-1 node (+ node 7) the answers
             ad = np.zeros_like(batch[6])

@@ -9,10 +9,12 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def names(prefix=""):
+def names(prefix="", include_lm=False):
+    """Golden case names.  ``include_lm``: also the language-model-encoder cases (``*_sbert_*``), which the CPU
+    oracle port does not restate (the HuggingFace encoder is the input of the path)."""
     out = sorted(os.path.splitext(os.path.basename(p))[0]
                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in out if n.startswith(prefix)]
+    return [n for n in out if n.startswith(prefix) and (include_lm or "sbert" not in n)]
 
 
 class Golden:
@@ -26,6 +28,8 @@ class Golden:
               b["weight_list"].tolist(), b["weight_rel_list"].tolist())
         self.batch = (b["local_entity"], b["query_entities"], kb, b["q_input"], b["seed_dist"], None,
                       b["answer_dist"])
+        self.rel_texts = b.get("rel_texts")
+        self.rel_texts_inv = b.get("rel_texts_inv")
         self.out = {k[4:]: z[k] for k in z.files if k.startswith("out/")}
         self.layer = {k[6:]: z[k] for k in z.files if k.startswith("layer/")}
         self.num_entity, self.num_relation, self.num_word = 1000, 40, 100

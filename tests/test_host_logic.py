@@ -14,7 +14,7 @@ from gnn_rag_b200 import parallel, synthetic as S
 from golden_io import Golden, names
 
 
-@pytest.mark.parametrize("name", names())
+@pytest.mark.parametrize("name", names(include_lm=True))
 def test_reference_state_dict_loads_strict(name):
     g = Golden(name)
     cls = G.NSM if g.args["model_name"] == "NSM" else G.ReaRev

@@ -11,7 +11,8 @@ import torch
 import gnn_rag_b200 as G
 from golden_io import GOLDEN_DIR, Golden
 
-CASES = ["rearev_small", "rearev_norm", "rearev_posemb", "rearev_sharp_ties", "nsm_small", "nsm_reason_kb"]
+CASES = ["rearev_small", "rearev_norm", "rearev_posemb", "rearev_sharp_ties", "nsm_small", "nsm_reason_kb",
+         "rearev_sbert_reltext"]
 
 
 def _load(name, device="cpu"):
@@ -22,6 +23,8 @@ def _load(name, device="cpu"):
     m = cls(args, g.num_entity, g.num_relation, g.num_word)
     m.load_state_dict(g.sd, strict=True)
     m.eval()                                            # dropout = identity, as in the generator
+    if g.rel_texts is not None:
+        m.encode_rel_texts(g.rel_texts, g.rel_texts_inv)
     batch = list(g.batch[:7])
     batch[6] = t["answer_dist"]
     return m, tuple(batch), t
