@@ -390,7 +390,7 @@ def run_ours(a):
         pass
     dense_ms = float(np.mean(dense)) if dense else float("nan")
     achieved = abytes / (dense_ms * 1e-3) / 1e9
-    agg_name = ("agg_abs_ws_kernel (gr_aggregate_dual_abs)" if ops.AGG_ABS and D == 200 and ops.TC_LINEAR
+    agg_name = ("agg_abs_wsg_kernel (gr_aggregate_dual_abs)" if ops.AGG_ABS and D == 200 and ops.TC_LINEAR
                 else "agg_kernel (gr_aggregate_dual)")
     roofline = {"bound": "hbm", "kernel": agg_name, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

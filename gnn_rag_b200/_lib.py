@@ -22,7 +22,7 @@ SIGNATURES = {
     "gr_csr_build_workspace_bytes": (c_size, [c_i64, c_i64]),
     "gr_csr_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64,
                              c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
-                             c_i32p, c_void_p, c_size, c_void_p]),
+                             c_i32p, c_i32p, c_void_p, c_size, c_void_p]),
     "gr_gather_f32": (c_int, [c_f32p, c_i32p, c_f32p, c_i64, c_void_p]),
     "gr_linear": (c_int, [c_f32p, c_i64, c_f32p, c_i64, c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_i64,
                           c_i64, c_i64, c_i64, c_u32, c_void_p]),
@@ -38,7 +38,7 @@ SIGNATURES = {
     "gr_pad_table256": (c_int, [c_f32p, c_i64, c_i64, c_int, c_f32p, c_void_p]),
     "gr_aggregate_dual_abs_supported": (c_int, [c_int, c_int, c_i64, c_i64]),
     "gr_aggregate_dual_abs": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p,
-                                     c_f32p, c_f32p, c_f32p, c_f32p, c_void_p, c_void_p, c_i64, c_i64, c_i64,
+                                     c_f32p, c_f32p, c_f32p, c_i64, c_f32p, c_void_p, c_void_p, c_i64, c_i64, c_i64,
                                      c_int, c_int, c_int, c_int, c_i64, c_i32p, c_void_p]),
     "gr_debug_store_probe": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_void_p]),
     "gr_type_layer": (c_int, [c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_i64,

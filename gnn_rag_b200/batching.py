@@ -50,8 +50,10 @@ def pin_batch(batch):
             pin(ad.astype(np.float32)))
 
 
-def stage_batch(batch, device, num_rel_rows, normalized_gnn=False, norm_rel=False):
-    """Copy one ``get_batch`` tuple to the device and build its CSRs.  Returns DeviceBatch."""
+def stage_batch(batch, device, num_rel_rows, normalized_gnn=False, norm_rel=False, nfacts=None):
+    """Copy one ``get_batch`` tuple to the device and build its CSRs.  Returns DeviceBatch.
+    ``nfacts``: optional int32[1] device tensor with the number of live facts when the fact arrays are fixed-capacity
+    buffers (GraphedStep); the weight lists, if used, must then have the same capacity."""
     if isinstance(batch, DeviceBatch):
         return batch
     local_entity, query_entities, kb_adj_mat, q_input, seed_dist, _true_batch_id, answer_dist = batch[:7]
@@ -73,16 +75,23 @@ def stage_batch(batch, device, num_rel_rows, normalized_gnn=False, norm_rel=Fals
     F = int(heads.shape[0])
     db.F = F
     dh, dr, dt = _to_dev(heads, device), _to_dev(rels, device), _to_dev(tails, device)
-    db.graph = ops.csr_build(dh, dr, dt, B, N, num_rel_rows)
+    db.graph = ops.csr_build(dh, dr, dt, B, N, num_rel_rows, nfacts)
     nbytes = (db.local_entity.numel() * 8 + db.q_input.numel() * 8 + 3 * B * N * 4
               + 3 * F * dh.element_size())
+    if (normalized_gnn and weight_list is None) or (norm_rel and weight_rel_list is None):
+        raise ValueError("normalized_gnn / norm_rel need kb_adj_mat's weight_list / weight_rel_list "
+                         "(the loader was built with weights='none'?)")
+
+    def wdev(w):
+        return w.to(device=device, dtype=torch.float32) if isinstance(w, torch.Tensor) \
+            else _to_dev(np.asarray(w, dtype=np.float32), device)
     if normalized_gnn and F > 0:      # COO values of build_matrix, base_gnn.py:38-41
-        w = _to_dev(np.asarray(weight_list, dtype=np.float32), device)
+        w = wdev(weight_list)
         db.graph.w_t = ops.gather_f32(w, db.graph.fact_t)
         db.graph.w_h = ops.gather_f32(w, db.graph.fact_h)
         nbytes += 4 * F
     if norm_rel and F > 0:            # TypeLayer values, layer_init.py:39-42
-        wr = _to_dev(np.asarray(weight_rel_list, dtype=np.float32), device)
+        wr = wdev(weight_rel_list)
         db.graph.wr_t = ops.gather_f32(wr, db.graph.fact_t)
         db.graph.wr_h = ops.gather_f32(wr, db.graph.fact_h)
         nbytes += 4 * F

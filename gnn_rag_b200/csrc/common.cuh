@@ -39,6 +39,16 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // number of SMs of the current device (148 on B200); cached
 int sm_count();
 
+// true the first time it is called for (flag array, current device): kernel attributes such as the dynamic
+// shared-memory opt-in are per device, a process may drive several
+inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 

@@ -20,10 +20,17 @@ __device__ __forceinline__ int64_t ld_idx(const void* p, int64_t i, int idx_byte
                         : (int64_t) reinterpret_cast<const int32_t*>(p)[i];
 }
 
+// `nfacts` (optional, device): the first *nfacts of the F slots hold facts, the rest is capacity padding of a
+// fixed-shape (CUDA-graph) buffer and is ignored.
+__device__ __forceinline__ int64_t live_facts(int64_t F, const int32_t* nfacts) {
+  return nfacts ? min(F, (int64_t)max(*nfacts, 0)) : F;
+}
+
 __global__ void hist_kernel(const void* __restrict__ heads, const void* __restrict__ rels,
                             const void* __restrict__ tails, int idx_bytes, int64_t F, int64_t Nt,
                             int64_t R1, int32_t* __restrict__ cnt_t, int32_t* __restrict__ cnt_h,
-                            int32_t* __restrict__ status) {
+                            int32_t* __restrict__ status, const int32_t* __restrict__ nfacts) {
+  F = live_facts(F, nfacts);
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < F; f += stride) {
     int64_t h = ld_idx(heads, f, idx_bytes), t = ld_idx(tails, f, idx_bytes);
@@ -130,7 +137,8 @@ __global__ void scan_add_kernel(int32_t* __restrict__ out0, int32_t* __restrict_
 __global__ void place_kernel(const void* __restrict__ heads, const void* __restrict__ tails,
                              int idx_bytes, int64_t F, int64_t Nt, int32_t* __restrict__ cur_t,
                              int32_t* __restrict__ cur_h, int32_t* __restrict__ fact_t,
-                             int32_t* __restrict__ fact_h) {
+                             int32_t* __restrict__ fact_h, const int32_t* __restrict__ nfacts) {
+  F = live_facts(F, nfacts);
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < F; f += stride) {
     int64_t h = ld_idx(heads, f, idx_bytes), t = ld_idx(tails, f, idx_bytes);
@@ -236,7 +244,9 @@ __global__ void fill_kernel(const void* __restrict__ heads, const void* __restri
                             int64_t Nt, int64_t R1,
                             const int32_t* __restrict__ fact_t, const int32_t* __restrict__ fact_h,
                             int32_t* __restrict__ src_t, int32_t* __restrict__ rel_t,
-                            int32_t* __restrict__ src_h, int32_t* __restrict__ rel_h) {
+                            int32_t* __restrict__ src_h, int32_t* __restrict__ rel_h,
+                            const int32_t* __restrict__ nfacts) {
+  F = live_facts(F, nfacts);
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < Fpad; e += stride) {
     if (e >= F) {   // padding slots: defined values so whole-chunk staging copies are benign
@@ -256,8 +266,10 @@ __global__ void fill_kernel(const void* __restrict__ heads, const void* __restri
 __global__ void gather_f32_kernel(const float* __restrict__ in, const int32_t* __restrict__ fact,
                                   float* __restrict__ out, int64_t F) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < F; e += stride)
-    out[e] = in[fact[e]];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < F; e += stride) {
+    const int64_t f = fact[e];                     // slots beyond the live fact count (capacity padding) hold garbage
+    out[e] = in[min(max(f, (int64_t)0), F - 1)];   // and are never read through the row pointers: keep the load in bounds
+  }
 }
 
 struct CsrWs {
@@ -296,7 +308,7 @@ extern "C" int gr_csr_build(const void* heads, const void* rels, const void* tai
                             int64_t F, int64_t Nt, int64_t num_rel_rows, int32_t* rowptr_t,
                             int32_t* src_t, int32_t* rel_t, int32_t* fact_t, int32_t* rowptr_h,
                             int32_t* src_h, int32_t* rel_h, int32_t* fact_h, int32_t* status,
-                            void* workspace, size_t workspace_bytes, void* stream_) {
+                            const int32_t* nfacts, void* workspace, size_t workspace_bytes, void* stream_) {
   using namespace gr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   GR_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "idx_bytes must be 4 or 8");
@@ -320,7 +332,7 @@ extern "C" int gr_csr_build(const void* heads, const void* rels, const void* tai
   int grid_f = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(F, threads), 1), 8LL * sm_count());
   if (F > 0) {
     hist_kernel<<<grid_f, threads, 0, stream>>>(heads, rels, tails, idx_bytes, F, Nt, num_rel_rows,
-                                                w.cur_t, w.cur_h, status);
+                                                w.cur_t, w.cur_h, status, nfacts);
     GR_CHECK_LAUNCH();
   }
   scan_local_kernel<<<dim3(nblocks, 2), kScanThreads, 0, stream>>>(w.cur_t, w.cur_h, rowptr_t,
@@ -333,7 +345,7 @@ extern "C" int gr_csr_build(const void* heads, const void* rels, const void* tai
   GR_CHECK_LAUNCH();
   if (F > 0) {
     place_kernel<<<grid_f, threads, 0, stream>>>(heads, tails, idx_bytes, F, Nt, w.cur_t, w.cur_h,
-                                                 fact_t, fact_h);
+                                                 fact_t, fact_h, nfacts);
     GR_CHECK_LAUNCH();
     int64_t rows2 = 2 * Nt;
     sort_rows_small_kernel<<<(unsigned)ceil_div(rows2, threads), threads, 0, stream>>>(
@@ -344,7 +356,7 @@ extern "C" int gr_csr_build(const void* heads, const void* rels, const void* tai
     GR_CHECK_LAUNCH();
     int64_t Fpad = gr_pad4(F);
     fill_kernel<<<grid_f, threads, 0, stream>>>(heads, rels, tails, idx_bytes, F, Fpad, Nt,
-                                                num_rel_rows, fact_t, fact_h, src_t, rel_t, src_h, rel_h);
+                                                num_rel_rows, fact_t, fact_h, src_t, rel_t, src_h, rel_h, nfacts);
     GR_CHECK_LAUNCH();
   }
   return GR_OK;

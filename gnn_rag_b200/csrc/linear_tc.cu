@@ -602,11 +602,10 @@ template <int CS, int BK>
 int launch_tc_cs(const CUtensorMap& m_a_hi, const CUtensorMap& m_a_lo, const CUtensorMap& m_w_hi,
                  const CUtensorMap& m_w_lo, const CUtensorMap& m_c, const CUtensorMap& m_c_hi,
                  const CUtensorMap& m_c_lo, const TcPlan& t, const TcParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[64] = {};
+  if (first_use_on_device(attr_done)) {
     GR_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<CS, BK>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
   }
   const int ngroups = (p.num_tiles + CS - 1) / CS;
   const int nclusters = std::max(1, std::min(ngroups, sm_count() / CS));

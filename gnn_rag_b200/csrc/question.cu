@@ -341,11 +341,10 @@ extern "C" int gr_instructions(const float* hidden, const float* qnode, const in
   p.B = B; p.Q = Q; p.D = D; p.I = I;
   const size_t smem = ((size_t)Q * D + (size_t)(I + 7) * D + 2 * (size_t)Q) * sizeof(float);
   GR_CHECK_ARG(smem <= 200 * 1024, "question length x entity_dim too large for shared memory");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[64] = {};
+  if (first_use_on_device(attr_done)) {
     GR_CHECK_CUDA(cudaFuncSetAttribute(instructions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        200 * 1024));
-    attr_set = true;
   }
   instructions_kernel<<<B, kQThreads, smem, stream>>>(p);
   GR_CHECK_LAUNCH();
@@ -508,10 +507,9 @@ extern "C" int gr_lstm_forward(const float* gates_x, const float* W_hh, const fl
   GR_CHECK_ARG(B > 0 && Q > 0 && D > 0 && D <= 256, "bad shape (hidden size <= 256)");
   const int U = (D + kLstmCluster - 1) / kLstmCluster;
   const size_t smem = ((size_t)4 * U * (D | 1) + 8 + (size_t)2 * D * kLstmQB + (size_t)4 * U * kLstmQB) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[64] = {};
+  if (first_use_on_device(attr_done)) {
     GR_CHECK_CUDA(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   GR_CHECK_ARG(smem <= 200 * 1024, "hidden size too large for shared memory");
   const int clusters = (B + kLstmQB - 1) / kLstmQB;

@@ -1,16 +1,24 @@
 """CUDA-graph execution of the whole hot-path step for fixed batch shapes.
 
-One step = CSR batching of the fact list -> model.forward -> candidate ranking.  It launches ~175 kernels, ~130
-of them tiny (question encoder, instruction updates, loss), so at WebQSP batch sizes the GPU idles between
-launches.  :class:`GraphedStep` captures the step once per input shape ``(B, N, F, Q)`` into a CUDA graph over
-static device buffers and replays it: per call it only copies the host batch into the static buffers (H2D from
-pinned or pageable memory), replays, and returns views of the static outputs.  Shapes that were not captured yet
-are captured on first use; the numerics are those of the eager path (same kernels, same order).
+One step = CSR batching of the fact list -> model.forward -> candidate ranking.  It launches ~70 kernels, most of
+them small, so at WebQSP batch sizes the GPU idles between launches.  :class:`GraphedStep` captures the step into a
+CUDA graph over static device buffers and replays it: per call it only copies the host batch into the static buffers
+(H2D from pinned or pageable memory), replays, and returns views of the static outputs.  The numerics are those of
+the eager path (same kernels, same order).
+
+Shapes.  A graph is fixed in ``(B, N, Q)`` and in the CAPACITY of its fact buffers.  ``get_batch`` returns a different
+fact count F for almost every batch (gnn/dataset_load.py:473-527), so capacities are bucketed (8 buckets per octave,
+<= 12.5 % padding): the batch's facts occupy the front of the buffers, a device-side counter tells the CSR build how
+many slots are live (``gr_csr_build(..., nfacts)``) and everything downstream sees live facts only, through the row
+pointers.  Captured graphs are kept in an LRU cache (``max_graphs``); the graph, its static buffers, landing buffers
+and pinned host buffers of an evicted entry are released.
 
 Serving loop: :meth:`GraphedStep.submit` / :meth:`GraphedStep.collect` pipeline two batches -- the H2D copy of
 batch i+1 (copy stream, into a landing buffer set) and the D2H read of batch i's results overlap the graph of
 batch i, so the end-to-end rate is bounded by the device time of the step, not by device + PCIe time.
 """
+import collections
+
 import numpy as np
 import torch
 
@@ -30,31 +38,40 @@ class Ticket:
     __slots__ = ("slot", "done", "ent", "local_entity_host", "B", "N")
 
 
+def fact_capacity(F):
+    """Bucketed capacity for a batch of F facts: next multiple of 2^(floor(log2 F) - 3), at least 1024."""
+    F = max(int(F), 1)
+    g = max(1 << max(F.bit_length() - 4, 0), 1024)
+    return (F + g - 1) // g * g
+
+
 class GraphedStep:
-    def __init__(self, model, num_entity, eps=None):
+    def __init__(self, model, num_entity, eps=None, max_graphs=8):
         self.model = model
         self.num_entity = num_entity
         self.eps = model.eps if eps is None else eps
         self.device = next(model.parameters()).device
-        self._cache = {}
+        self.max_graphs = max_graphs
+        self._cache = collections.OrderedDict()
         self._copy_stream = None      # H2D stream
         self._d2h_stream = None       # separate: a D2H waiting for graph i must not block the H2D of batch i+1
         self._slot = 0
+        self._weights = bool(model.normalized_gnn), bool(model.norm_rel)
 
     # -- the work that gets captured ------------------------------------------------------------------------
     def _run(self, st):
         m = self.model
-        tup = (st.local_entity, st.query_entities, (st.heads, st.rels, st.tails, None, None, None, None),
+        tup = (st.local_entity, st.query_entities,
+               (st.heads, st.rels, st.tails, None, None, st.weight_list, st.weight_rel_list),
                st.q_input, st.seed_dist, None, st.answer_dist)
-        db = batching.stage_batch(tup, self.device, m.num_relation + 1, False, False)
+        db = batching.stage_batch(tup, self.device, m.num_relation + 1, m.normalized_gnn, m.norm_rel,
+                                  nfacts=st.nfacts)
         loss, pred, pred_dist, _ = m(db)
         cand_idx, cand_count, cand_total = ops.rank_candidates(pred_dist, db.local_entity, db.query_entities,
                                                               self.num_entity, self.eps)
         return db, loss, pred, pred_dist, cand_idx, cand_count, cand_total
 
-    def _capture(self, B, N, F, Q, idx_dtype):
-        if self.model.normalized_gnn or self.model.norm_rel:
-            raise NotImplementedError("GraphedStep: per-fact weight lists (normalized_gnn / norm_rel) not wired")
+    def _static_inputs(self, B, N, cap, Q, idx_dtype):
         dev = self.device
         st = _Captured()
         st.local_entity = torch.zeros(B, N, dtype=torch.int64, device=dev)
@@ -62,63 +79,111 @@ class GraphedStep:
         st.seed_dist = torch.zeros(B, N, dtype=torch.float32, device=dev)
         st.answer_dist = torch.zeros(B, N, dtype=torch.float32, device=dev)
         st.q_input = torch.zeros(B, Q, dtype=torch.int64, device=dev)
-        st.heads = torch.zeros(F, dtype=idx_dtype, device=dev)
-        st.rels = torch.zeros(F, dtype=idx_dtype, device=dev)
-        st.tails = torch.zeros(F, dtype=idx_dtype, device=dev)
+        st.heads = torch.zeros(cap, dtype=idx_dtype, device=dev)
+        st.rels = torch.zeros(cap, dtype=idx_dtype, device=dev)
+        st.tails = torch.zeros(cap, dtype=idx_dtype, device=dev)
+        st.nfacts = torch.zeros(1, dtype=torch.int32, device=dev)
+        st.weight_list = torch.ones(cap, dtype=torch.float32, device=dev) if self._weights[0] else None
+        st.weight_rel_list = torch.ones(cap, dtype=torch.float32, device=dev) if self._weights[1] else None
         return st
 
+    def _names(self):
+        names = ["local_entity", "query_entities", "seed_dist", "answer_dist", "q_input", "heads", "rels", "tails",
+                 "nfacts"]
+        if self._weights[0]:
+            names.append("weight_list")
+        if self._weights[1]:
+            names.append("weight_rel_list")
+        return names
+
     def _fill(self, st, batch):
+        """Host batch -> the buffers of ``st`` (facts to the front of the capacity, live count to ``nfacts``)."""
         le, qe, kb, qi, sd, _, ad = batch[:7]
+        F = int(kb[0].shape[0])
+
+        def host(src, dtype):
+            t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(src)))
+            if t.dtype != dtype and not t.is_cuda:
+                t = t.to(dtype)
+            return t
 
         def put(dst, src):
-            t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src))
-            if t.dtype != dst.dtype and not t.is_cuda:
-                t = t.to(dst.dtype)
-            dst.copy_(t, non_blocking=True)
+            dst.copy_(host(src, dst.dtype), non_blocking=True)
+
+        def put_front(dst, src):
+            dst[:F].copy_(host(src, dst.dtype), non_blocking=True)
         put(st.local_entity, le); put(st.query_entities, qe); put(st.seed_dist, sd); put(st.answer_dist, ad)
-        put(st.q_input, qi); put(st.heads, kb[0]); put(st.rels, kb[1]); put(st.tails, kb[2])
+        put(st.q_input, qi)
+        put_front(st.heads, kb[0]); put_front(st.rels, kb[1]); put_front(st.tails, kb[2])
+        if st.weight_list is not None:
+            if kb[5] is None:
+                raise ValueError("normalized_gnn needs kb_adj_mat's weight_list")
+            put_front(st.weight_list, np.asarray(kb[5], dtype=np.float32) if not isinstance(kb[5], torch.Tensor) else kb[5])
+        if st.weight_rel_list is not None:
+            if kb[6] is None:
+                raise ValueError("norm_rel needs kb_adj_mat's weight_rel_list")
+            put_front(st.weight_rel_list,
+                      np.asarray(kb[6], dtype=np.float32) if not isinstance(kb[6], torch.Tensor) else kb[6])
+        st.nfacts.copy_(torch.tensor([F], dtype=torch.int32), non_blocking=True)
+        idx_b = st.heads.element_size()
+        self._h2d_bytes = (st.local_entity.numel() * 8 + st.q_input.numel() * 8 + 3 * st.seed_dist.numel() * 4
+                           + 3 * F * idx_b + 4 + 4 * F * (int(st.weight_list is not None) +
+                                                          int(st.weight_rel_list is not None)))
 
     def _entry(self, batch):
         le, kb, qi = batch[0], batch[2], batch[3]
         B, N = le.shape
-        F = int(kb[0].shape[0])
+        cap = fact_capacity(int(kb[0].shape[0]))
         Q = int(qi.shape[1])
         idx_dtype = torch.int32 if str(kb[0].dtype).endswith("int32") else torch.int64
         # parameter versions are part of the key: the captured graph holds pre-formatted (split-bf16) weights
-        key = (B, N, F, Q, idx_dtype, sum(p._version for p in self.model.parameters()))
+        key = (B, N, cap, Q, idx_dtype, sum(p._version for p in self.model.parameters()))
         ent = self._cache.get(key)
-        if ent is None:
-            st = self._capture(B, N, F, Q, idx_dtype)
-            self._fill(st, batch)
+        if ent is not None:
+            self._cache.move_to_end(key)
+            return ent
+        while len(self._cache) >= self.max_graphs:          # LRU eviction: graph, static + landing + pinned buffers
+            _k, old = self._cache.popitem(last=False)
             torch.cuda.synchronize()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):            # warm-up on a side stream (lazy init, allocator, caches)
-                for _ in range(2):
-                    self._run(st)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                outs = self._run(st)
-            ent = _Captured()
-            ent.st, ent.g, ent.outs = st, g, outs
-            ent.pipe = None
-            self._cache[key] = ent
+            del old
+        st = self._static_inputs(B, N, cap, Q, idx_dtype)
+        self._fill(st, batch)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up on a side stream (lazy init, allocator, caches)
+            for _ in range(2):
+                self._run(st)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs = self._run(st)
+        ent = _Captured()
+        ent.st, ent.g, ent.outs = st, g, outs
+        ent.pipe = None
+        ent.weight_ws = ops.live_weight_workspaces()        # the graph reads these pre-formatted weights: keep them alive
+        self._cache[key] = ent
         return ent
 
-    def __call__(self, batch):
+    @staticmethod
+    def _check(db):
+        """ids outside the batch are clamped by the CSR build and flagged (a malformed / mis-sharded fact list)."""
+        db.graph.check_status()
+
+    def __call__(self, batch, check=False):
         ent = self._entry(batch)
         self._fill(ent.st, batch)
         ent.g.replay()
         o = StepOutput()
         o.db, o.loss, o.pred, o.pred_dist, o.cand_idx, o.cand_count, o.cand_total = ent.outs
+        o.db.h2d_bytes = self._h2d_bytes
         self.model.last_batch = o.db
+        if check:
+            self._check(o.db)
         return o
 
     # -- two-deep pipeline: H2D of batch i+1 and D2H of batch i overlap the graph of batch i -----------------
-    _IN = ("local_entity", "query_entities", "seed_dist", "answer_dist", "q_input", "heads", "rels", "tails")
-
     def _pipe(self, ent):
         if ent.pipe is None:
             if self._copy_stream is None:
@@ -130,12 +195,14 @@ class GraphedStep:
             pipe.land_free, pipe.done = [], []
             for _ in range(2):
                 land = _Captured()
-                for name in self._IN:
+                for name in self._names():
                     setattr(land, name, torch.empty_like(getattr(ent.st, name)))
+                land.weight_list = getattr(land, "weight_list", None)
+                land.weight_rel_list = getattr(land, "weight_rel_list", None)
                 pipe.land.append(land)
                 od = dict(cand_idx=torch.empty_like(cand_idx), pred_dist=torch.empty_like(pred_dist),
                           cand_count=torch.empty_like(cand_count), pred=torch.empty_like(pred),
-                          loss=torch.empty_like(loss))
+                          loss=torch.empty_like(loss), status=torch.empty_like(db.graph.status))
                 pipe.out_dev.append(od)
                 pipe.out_host.append({k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
                                       for k, v in od.items()})
@@ -161,7 +228,7 @@ class GraphedStep:
             h2d_done = torch.cuda.Event()
             h2d_done.record(cs)
         cur.wait_event(h2d_done)
-        for name in self._IN:                        # landing set -> the graph's static inputs (D2D, ~10 us)
+        for name in self._names():                   # landing set -> the graph's static inputs (D2D, ~10 us)
             getattr(ent.st, name).copy_(getattr(land, name), non_blocking=True)
         pipe.land_free[slot] = torch.cuda.Event()
         pipe.land_free[slot].record(cur)
@@ -173,6 +240,7 @@ class GraphedStep:
         od["cand_count"].copy_(cand_count, non_blocking=True)
         od["pred"].copy_(pred, non_blocking=True)
         od["loss"].copy_(loss, non_blocking=True)
+        od["status"].copy_(db.graph.status, non_blocking=True)
         out_ready = torch.cuda.Event()
         out_ready.record(cur)
         ds = self._d2h_stream
@@ -182,6 +250,7 @@ class GraphedStep:
                 pipe.out_host[slot][k].copy_(v, non_blocking=True)
             pipe.done[slot] = torch.cuda.Event()
             pipe.done[slot].record(ds)
+        db.h2d_bytes = self._h2d_bytes
         self.model.last_batch = db
         t = Ticket()
         t.slot, t.done, t.ent = slot, pipe.done[slot], ent
@@ -192,10 +261,13 @@ class GraphedStep:
 
     def collect(self, ticket):
         """Wait for a submitted step and return (retrieved, d2h_bytes, loss, pred): the ordered candidate lists
-        of every question (like :func:`evaluate.retrieve`), the bytes read back, the loss and the argmax."""
+        of every question (like :func:`evaluate.retrieve`), the bytes read back, the loss and the argmax.
+        Raises if the CSR build flagged node / relation ids outside the batch."""
         from .evaluate import Retrieved
         ticket.done.synchronize()
         h = ticket.ent.pipe.out_host[ticket.slot]
+        if int(h["status"][0]) != 0:
+            raise RuntimeError("fact list contains node/relation ids outside the batch (clamped)")
         idx_h, dist_h = h["cand_idx"].numpy(), h["pred_dist"].numpy()
         counts = h["cand_count"].numpy()
         le = ticket.local_entity_host
@@ -210,6 +282,7 @@ class GraphedStep:
         """Ordered candidate lists of a :class:`StepOutput` (one D2H), like evaluate.retrieve."""
         from .evaluate import Retrieved
         counts_h = out.cand_count.cpu().numpy()
+        self._check(out.db)
         maxc = int(counts_h.max()) if counts_h.size else 0
         ei, ef = np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float32)
         if maxc == 0:

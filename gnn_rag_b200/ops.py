@@ -109,8 +109,10 @@ class CsrGraph:
             raise RuntimeError("fact list contains node/relation ids outside the batch (clamped)")
 
 
-def csr_build(heads, rels, tails, B, N, R1):
-    """heads/rels/tails: 1-D int64 or int32 CUDA tensors (global rows b*N+local) -> CsrGraph."""
+def csr_build(heads, rels, tails, B, N, R1, nfacts=None):
+    """heads/rels/tails: 1-D int64 or int32 CUDA tensors (global rows b*N+local) -> CsrGraph.
+    ``nfacts``: optional int32[1] device tensor -- only the first ``nfacts`` slots are facts, the rest is capacity
+    padding of fixed-shape buffers (GraphedStep)."""
     heads, rels, tails = _cuda(heads, name="heads"), _cuda(rels, name="rels"), _cuda(tails, name="tails")
     if heads.dtype not in (torch.int64, torch.int32) or rels.dtype != heads.dtype or tails.dtype != heads.dtype:
         raise RuntimeError("fact arrays must share dtype int64 or int32")
@@ -123,7 +125,7 @@ def csr_build(heads, rels, tails, B, N, R1):
                         heads.element_size(), F, B * N, R1,
                         _p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(g.fact_t),
                         _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(g.fact_h),
-                        _p(g.status), _p(ws), ws_bytes, _stream())
+                        _p(g.status), _p(nfacts), _p(ws), ws_bytes, _stream())
     _lib.check(rc)
     STATS.launches += 9 if F > 0 else 5     # memsets excluded: hist, 3x scan, place, 2x sort, fill (+gather)
     return g
@@ -279,7 +281,8 @@ def aggregate_dual_abs(g, prior, pn_fwd, pn_inv, ins, planes, out_col0, seg_pitc
     with _AggTimer(("dual", I)):
         rc = _L().gr_aggregate_dual_abs(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t),
                                        _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(w_h),
-                                       _p(prior), _p(pn_fwd), _p(pn_inv), _p(ins), _p(hi), _p(lo), hi.stride(0),
+                                       _p(prior), _p(pn_fwd), _p(pn_inv), pn_fwd.shape[0], _p(ins), _p(hi), _p(lo),
+                                       hi.stride(0),
                                        out_col0, seg_pitch, B, g.N, D, I, g.F, _p(_TILE_COUNTER[dev]), _stream())
     _lib.check(rc)
     STATS.launches += (I + 3) // 4
@@ -362,8 +365,17 @@ def param_planes(P):
 
 
 def clear_weight_cache():
+    """Drop the cached pre-formatted weights.  Captured CUDA graphs keep their own references to the workspaces they
+    read (:func:`live_weight_workspaces`), so clearing the cache never frees memory a graph replay still uses.
+    Note: the caches are validated by ``tensor._version``; in-place writes through ``.data`` (``p.data.copy_``,
+    ``p.data.mul_``) do not bump it -- call this function after such updates."""
     _W_CACHE.clear()
     _P_CACHE.clear()
+
+
+def live_weight_workspaces():
+    """Strong references to every cached pre-formatted weight buffer (held by GraphedStep entries)."""
+    return [e[0] for e in _W_CACHE.values()] + [t for e in _P_CACHE.values() for t in e[:2]]
 
 
 def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=None, dots=None, relu=True,

@@ -68,6 +68,9 @@ static inline int64_t gr_pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
  * pure function of the row's own fact sequence (deterministic; ties stay ties).
  *   rowptr_*: int32[Nt+1]; src_*, rel_*, fact_*: int32[F] (fact_* = original fact id of each slot).
  *   status: int32[1], set non-zero on device if an id is out of range (ids are clamped).
+ *   nfacts: optional device int32[1].  When given, only the first min(F, *nfacts) fact slots are read: F is then the
+ *   CAPACITY of fixed-shape input buffers (CUDA-graph replay over batches of different fact counts); everything
+ *   downstream sees the live facts only, through the row pointers.
  * Workspace: gr_csr_build_workspace_bytes(F, Nt).
  */
 size_t gr_csr_build_workspace_bytes(int64_t F, int64_t Nt);
@@ -75,7 +78,7 @@ int gr_csr_build(const void* heads, const void* rels, const void* tails, int idx
                  int64_t F, int64_t Nt, int64_t num_rel_rows,
                  int32_t* rowptr_t, int32_t* src_t, int32_t* rel_t, int32_t* fact_t,
                  int32_t* rowptr_h, int32_t* src_h, int32_t* rel_h, int32_t* fact_h,
-                 int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+                 int32_t* status, const int32_t* nfacts, void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[e] = in[fact[e]] -- permute a per-fact fp32 array (weight_list / weight_rel_list of
  * gnn/dataset_load.py:509-517) into CSR slot order. */
@@ -177,12 +180,15 @@ int gr_pad_table256(const float* table, int64_t ldt, int64_t rows, int D, float*
 int gr_aggregate_dual_abs_supported(int N, int D, int64_t seg_pitch, int64_t R1);
 int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
                          const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
-                         const float* prior, const float* pn_fwd, const float* pn_inv, const float* ins,
-                         void* out_hi, void* out_lo, int64_t ld_planes, int64_t out_col0, int64_t seg_pitch,
-                         int B, int N, int D, int I, int64_t F, int32_t* tile_counter, void* stream);
-/* tile_counter: 4 bytes of device scratch (zeroed by the call) -> the persistent, warp-specialised kernel (a producer
- * warp stages the next 64-row tile while eight consumer warps aggregate the current one; dynamic tile scheduler);
- * NULL -> one CTA per tile. */
+                         const float* prior, const float* pn_fwd, const float* pn_inv, int64_t table_rows,
+                         const float* ins, void* out_hi, void* out_lo, int64_t ld_planes, int64_t out_col0,
+                         int64_t seg_pitch, int B, int N, int D, int I, int64_t F, int32_t* tile_counter, void* stream);
+/* table_rows: rows (R1) of each padded table.
+ * tile_counter: 4 bytes of device scratch (zeroed by the call) -> the persistent, warp-specialised kernel (a staging
+ * warp prepares the next tile of rows while the consumer warps aggregate the current one; dynamic tile scheduler);
+ * NULL -> one CTA per 64-row tile.  gr_set_option("agg_abs_ws", v) picks the persistent variant: 1 = 8 consumer warps /
+ * 64-row tiles, 2 (default) = 9 consumer warps / 72-row tiles, 3 = gather through TMA tile::gather4 copies into
+ * shared-memory rings (bit-identical results; slower at cfg2, kept as the measured alternative). */
 
 /* Diagnostic only (scripts/agg_probe.py): replays the aggregation kernel's store pattern without any edge work. */
 int gr_debug_store_probe(void* hi, void* lo, int64_t Nt, int64_t ld, int col_start, int ncols, int mode,

@@ -31,8 +31,6 @@ abytes = 2 * F * 8 + 2 * (B * N + 1) * 4 + B * N * 4 + 2 * (R + 1) * D * 4 + B *
 
 def run(mode, hot, planes):
     ops.set_option("agg_abs_ws", mode)
-    ops.set_option("agg_hot_rel", hot)
-    ops.set_option("agg_table_rows", R + 1)
     ops.aggregate_dual_abs(g, prior, pf, pi, ins, planes, 208, 208)
 
 
@@ -50,13 +48,13 @@ def timeit(mode, hot, planes, n=20):
     return ts[len(ts) // 2], ts[0]
 
 
-modes = [int(x) for x in sys.argv[1:]] or [1, 6, 2]
+modes = [int(x) for x in sys.argv[1:]] or [0, 1, 2, 3]
 ref = [torch.full((B * N, Kp), 7.0, dtype=torch.bfloat16, device=dev) for _ in range(2)]
 run(1, -1, tuple(ref))
 torch.cuda.synchronize()
 res = {}
 for mode in modes:
-    for hot in ([-1] if mode < 3 else [-1, R - 1]):
+    for hot in [-1]:
         got = [torch.full((B * N, Kp), 7.0, dtype=torch.bfloat16, device=dev) for _ in range(2)]
         run(mode, hot, tuple(got))
         torch.cuda.synchronize()
@@ -66,7 +64,6 @@ for mode in modes:
                                                 GBps=abytes / med / 1e3, frac=abytes / med / 1e3 / 6568.0)
         print("mode %d hot %5d  bit-equal %s  %.1f us (min %.1f)  %.0f GB/s  frac %.3f" % (
             mode, hot, same, med, best, abytes / med / 1e3, abytes / med / 1e3 / 6568.0), flush=True)
-ops.set_option("agg_abs_ws", 1)
-ops.set_option("agg_hot_rel", -1)
+ops.set_option("agg_abs_ws", 2)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/agg_modes_probe.json", "w"), indent=1)

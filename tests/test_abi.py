@@ -72,7 +72,7 @@ def test_argument_validation_returns_status_codes():
     rc = lib.gr_linear(None, 4, None, 4, None, None, 0, 0, None, 4, 4, 4, 4, 0, None)
     assert rc == -1 and b"null pointer" in lib.gr_last_error()
     rc = lib.gr_csr_build(None, None, None, 3, 0, 10, 5, None, None, None, None, None, None, None, None,
-                          None, None, 0, None)
+                          None, None, None, 0, None)
     assert rc == -1 and b"idx_bytes" in lib.gr_last_error()
     rc = lib.gr_set_option(b"no_such_option", 1)
     assert rc == -1
@@ -90,5 +90,6 @@ def test_models_refuse_cpu():
     m = G.ReaRev(args, 100, 10, 20)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(S.make_batch(0, 2, 10, 20, 100, 10, 20))
-    with pytest.raises(NotImplementedError):
-        m(S.make_batch(0, 2, 10, 20, 100, 10, 20), training=True)
+    # training=True is the differentiable torch path (autograd_path.py): plain torch, any device
+    loss, pred, dist, tp = m(S.make_batch(0, 2, 10, 20, 100, 10, 20), training=True)
+    assert loss.requires_grad and len(tp) == 2

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import gnn_rag_b200 as G
-from gnn_rag_b200 import batching, evaluate, ops, synthetic as S
+from gnn_rag_b200 import batching, evaluate, graphed, ops, synthetic as S
 from oracle import kgqa_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -167,6 +167,49 @@ def test_graphed_step_matches_eager():
         assert torch.equal(dist_g, dist)
         assert float(out.loss) == float(loss)
         assert [r.ent.tolist() for r in ret_g] == [r.ent.tolist() for r in ret_e]
+
+
+def test_graphed_step_buckets_fact_counts_and_evicts():
+    """Real ``get_batch`` output has a different fact count almost every batch: batches whose counts fall into one
+    capacity bucket replay ONE captured graph (facts in front, device-side live count) and still equal the eager
+    path bit for bit; the cache is an LRU of ``max_graphs`` entries; ids outside the batch are reported."""
+    c = dict(S.CONFIGS["cfg2"], B=6, N=400, E=1300)
+    m, args = _model(c)
+    gs = G.GraphedStep(m, S.WEBQSP_NUM_ENTITY, max_graphs=2)
+    caps = set()
+    for seed, E in ((31, 1300), (32, 1250), (33, 1350), (34, 700), (35, 2600), (36, 1300)):
+        b = S.make_batch(seed, B=c["B"], N=c["N"], E=E, with_weights=False)
+        F = len(b[2][0])
+        caps.add(graphed.fact_capacity(F))
+        assert graphed.fact_capacity(F) >= F and graphed.fact_capacity(F) <= 1.13 * F + 1024
+        out = gs(b)
+        dist_g = out.pred_dist.clone()
+        ret_g, _ = gs.retrieve(out)
+        _, _, dist, _ = m(b)
+        ret_e, _ = evaluate.retrieve(dist, m.last_batch, S.WEBQSP_NUM_ENTITY, args["eps"])
+        assert torch.equal(dist_g, dist)
+        assert [r.ent.tolist() for r in ret_g] == [r.ent.tolist() for r in ret_e]
+        assert len(gs._cache) <= 2
+    assert len(caps) >= 3                                         # several buckets were exercised -> evictions
+    bad = S.make_batch(37, B=c["B"], N=c["N"], E=1300, with_weights=False)
+    bad[2][0][5] = c["B"] * c["N"] + 3                           # a head id outside the batch
+    with pytest.raises(RuntimeError, match="outside the batch"):
+        gs.retrieve(gs(bad))
+
+
+def test_graphed_step_with_edge_weights():
+    """normalized_gnn / norm_rel weight lists ride along in the captured step (fixed-capacity buffers)."""
+    args = S.model_args("ReaRev", entity_dim=200, num_iter=2, num_ins=2, num_gnn=2, use_cuda=True,
+                        normalized_gnn=True, norm_rel=True)
+    torch.manual_seed(0)
+    m = G.ReaRev(dict(args), 3000, 40, 100).eval()
+    gs = G.GraphedStep(m, 3000)
+    for seed in (41, 42):
+        b = S.make_batch(seed, B=4, N=128, E=500 + 10 * seed, num_entity=3000, num_relation=40, num_word=100)
+        out = gs(b)
+        dist_g = out.pred_dist.clone()
+        _, _, dist, _ = m(b)
+        assert torch.equal(dist_g, dist)
 
 
 def test_graphed_pipeline_submit_collect_matches_sync():

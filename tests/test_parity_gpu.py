@@ -267,7 +267,7 @@ def test_aggregate_deterministic_and_tma_identical():
     assert torch.equal(outs[0], outs[2])          # TMA-staged variant bit identical to plain staging
 
 
-@pytest.mark.parametrize("ws", [1, 0])
+@pytest.mark.parametrize("ws", [2, 1, 0, 3])
 @pytest.mark.parametrize("I,normalized", [(2, False), (2, True), (1, False), (3, True), (5, False)])
 def test_aggregate_abs_kernel_matches_generic_kernel(I, normalized, ws):
     """|v|-accumulating aggregation (csrc/aggregate_abs.cu) == the generic kernel's planes:
@@ -310,7 +310,7 @@ def test_aggregate_abs_kernel_matches_generic_kernel(I, normalized, ws):
             seg = a.view(B * N, 2 * I, 208)
             assert (seg[:, :, 200:] == 0).all()               # padding columns written as zeros
     finally:
-        ops.set_option("agg_abs_ws", 1)
+        ops.set_option("agg_abs_ws", 2)
 
 
 def test_type_layer_vs_oracle():
@@ -519,7 +519,7 @@ def test_forward_vs_oracle_webqsp_shape(model, kw):
     assert torch.allclose(dist.sum(1).cpu(), torch.ones(4), atol=1e-5)
     got, _ = evaluate.retrieve(dist, m.last_batch, 5000, 0.95)
     ref = O.rank_candidates(b[0], b[1], want.numpy(), 5000, 0.95)
-    assert_ranking_equivalent(got, ref, want.numpy())
+    assert_ranking_equivalent(got, ref, want.numpy(), name="oracle_forward")
 
 
 def test_full_size_properties_cfg2():
