@@ -37,8 +37,18 @@ WORKLOADS = {
     "cfg1": "single WebQSP question, ~2k-node/~6k-edge subgraph, 3-hop ReaRev fp32",
     "cfg2": "batch=64 WebQSP-shape synthetic subgraphs (~2k nodes, 200-dim feat, 3 hops) on 1xB200",
     "cfg3": "batch=256 CWQ-shape synthetic subgraphs (~10k nodes, ~40k edges, 4 hops)",
+    "cfg4": "batch=1024 WebQSP-shape subgraphs sharded across 8xB200 = 128 questions per GPU (weak scaling)",
     "cfg5": "stress: 100k-node / 1M-edge synthetic subgraph, 400-dim feat, 3 hops",
 }
+
+
+def per_gpu_config(name):
+    """Per-GPU shape of a named workload: cfg4 is the 1024-question batch split over 8 GPUs, i.e. 128 per GPU
+    whatever --gpus is (weak scaling); every other config is per GPU as written."""
+    c = dict(S.CONFIGS[name])
+    if name == "cfg4":
+        c["B"] = c["B"] // 8
+    return c
 
 
 def parse():
@@ -48,7 +58,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=8, help="questions in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="questions per CPU step (default: 8 for the cpu_baseline leg, the whole batch -- at most 64 -- "
+                         "for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agg-tma", type=int, default=None)
     ap.add_argument("--agg-abs", type=int, default=None, help="0: generic aggregation kernel instead of the |v|-accumulating one")
@@ -70,8 +82,11 @@ def make_cfg_batch(c, seed, B=None):
     return S.make_batch(seed, B=B, N=c["N"], E=c["E"], with_weights=False)
 
 
-def config_dict(name, c, extra=None):
-    d = {"workload": "%s: %s" % (name, WORKLOADS[name]), "questions_per_gpu": c["B"], "nodes": c["N"],
+def config_dict(name, c, extra=None, world=1):
+    wl = "%s: %s" % (name, WORKLOADS[name])
+    if world > 1 or name == "cfg4":
+        wl += " -- weak scaling at %d questions per GPU" % c["B"]
+    d = {"workload": wl, "questions_per_gpu": c["B"], "nodes": c["N"],
          "kg_edges": c["E"], "facts_incl_self_loops": c["E"] + c["N"], "feat_dim": c["D"],
          "num_iter": c["T"], "num_gnn": c["K"], "num_ins": c["I"],
          "relations": S.WEBQSP_NUM_RELATION, "seeds": {"data": 1, "weights": 0}}
@@ -83,7 +98,7 @@ def config_dict(name, c, extra=None):
 # ---------------------------------------------------------------------------------------------------
 # CPU oracle port (cpu_baseline / --impl reference)
 # ---------------------------------------------------------------------------------------------------
-def cpu_oracle_run(c, sd_cpu, nq, steps, warmup):
+def cpu_oracle_run(c, sd_cpu, nq, steps, warmup, with_loader=True):
     """Time the oracle port (oracle/kgqa_oracle.py: the reference's op sequence on torch-CPU) on `nq`
     questions of the workload with all host threads.  Returns (questions/s, ms/step, cores)."""
     from oracle import kgqa_oracle as O
@@ -105,7 +120,7 @@ def cpu_oracle_run(c, sd_cpu, nq, steps, warmup):
     cores = best[0]
     torch.set_num_threads(cores)
     batch = make_cfg_batch(c, 1, B=nq)
-    times = []
+    times, loader_s = [], None
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
@@ -114,8 +129,19 @@ def cpu_oracle_run(c, sd_cpu, nq, steps, warmup):
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
+    if with_loader:
+        # the reference's get_batch cost for the same questions (oracle/loader_oracle.py: _build_fact_mat in the
+        # reference's own form), SURVEY 8d (ii): forward + get_batch + ranking
+        from oracle import loader_oracle
+        st = loader_oracle.state_from_batch(batch, S.WEBQSP_NUM_RELATION)
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        loader_oracle.build_fact_mat(st, list(range(nq)), 0.0)
+        loader_s = time.perf_counter() - t0
     tot = sum(times)
-    return nq * len(times) / tot, 1e3 * tot / len(times), cores
+    qps = nq * len(times) / tot
+    qps_with_loader = nq / (tot / len(times) + loader_s) if loader_s is not None else None
+    return qps, 1e3 * tot / len(times), cores, qps_with_loader
 
 
 def init_state_dict_cpu(c):
@@ -127,20 +153,27 @@ def init_state_dict_cpu(c):
 
 
 def run_reference(a):
+    """The reference's own CPU implementation of the path (the oracle port: /root/reference does not exist on the GPU
+    box and the reference is pure Python, so there is no oracle/_ref binary), all host threads, on this arm's config.
+    One step = forward + ranking of `sample` questions of the workload (the whole batch for cfg1 / cfg2 / cfg4)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    c = S.CONFIGS[a.config]
+    c = per_gpu_config(a.config)
     sd = init_state_dict_cpu(c)
-    nq = min(a.cpu_sample, c["B"])
-    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
-    qps, ms, cores = cpu_oracle_run(c, sd, nq, steps, warmup)
-    sample = "%d of %d questions per step, %d timed steps" % (nq, c["B"], steps)
+    default_nq = {"cfg3": 2, "cfg5": 1}.get(a.config, min(c["B"], 64))
+    nq = min(a.cpu_sample if a.cpu_sample else default_nq, c["B"])
+    heavy = a.config in ("cfg3", "cfg5")
+    steps = max(1, min(a.steps, 1 if heavy else 2))
+    warmup = 0 if heavy else max(1, min(a.warmup, 1))
+    qps, ms, cores, qps_l = cpu_oracle_run(c, sd, nq, steps, warmup)
+    sample = "%d of %d questions per step, %d timed step(s), %d warm-up" % (nq, c["B"], steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(a.config, c),
-            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": config_dict(a.config, c, {"sample": sample, "questions_per_step": nq}),
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "with_get_batch": qps_l},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -225,7 +258,7 @@ def run_ours(a):
         ops.set_option("tc_bk", a.tc_bk)
     if a.tc_cluster is not None:
         ops.set_option("tc_cluster", a.tc_cluster)
-    c = S.CONFIGS[a.config]
+    c = per_gpu_config(a.config)
     B, N, D, I = c["B"], c["N"], c["D"], c["I"]
     args = model_args_for(c, True)
     torch.manual_seed(0)
@@ -276,13 +309,28 @@ def run_ours(a):
     # graph in the timed region below, where per-launch events cannot be recorded
     ops.STATS.reset()
     ops.STATS.time_agg = True
+    ops.STATS.time_ops = True
+    rep_evs = []
     for _ in range(a.steps):
         flush.fill_(1)
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
         step_eager(dev_batch)
+        e0.record()
+        rep_evs.append((s0, e0))
     barrier()
     ops.STATS.time_agg = False
+    ops.STATS.time_ops = False
     launches = ops.STATS.launches
     agg = [(s.elapsed_time(e), tag) for s, e, tag in ops.STATS.agg_events]
+    # per-kernel-class device time of the eager replica (events around every wrapper, on the launching stream)
+    op_ms, gemm = {}, {}
+    for s_, e_, cls, info in ops.STATS.op_events:
+        ms = s_.elapsed_time(e_)
+        op_ms[cls] = op_ms.get(cls, 0.0) + ms
+        if cls == "gemm_tc":
+            gemm.setdefault(info, []).append(ms)
+    rep_ms = sum(s_.elapsed_time(e_) for s_, e_ in rep_evs)
     for _ in range(3):
         step(dev_batch)
     barrier()
@@ -350,11 +398,32 @@ def run_ours(a):
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e_mode = "synchronous"
+    # ---- e2e from what the loader returns: pageable numpy tuples (int64 facts, float64 distributions), a different
+    # batch every step, conversion + pinning-free H2D inside the timed region --------------------------------
+    e2e_pg_s, h2d_pg = float("nan"), 0
+    if gs is not None:
+        pool = [make_cfg_batch(c, 100 + rank * 16 + i) for i in range(4)]
+        for hb in pool[:2]:
+            gs.collect(gs.submit(hb))
+        barrier()
+        t0 = time.perf_counter()
+        prev = None
+        for i in range(a.steps):
+            tk = gs.submit(pool[i % len(pool)])
+            if world > 1:
+                parallel.all_gather_scores(tk.ent.outs[3], B * world)
+            if prev is not None:
+                gs.collect(prev)
+            prev = tk
+        gs.collect(prev)
+        h2d_pg = model.last_batch.h2d_bytes
+        barrier()
+        e2e_pg_s = time.perf_counter() - t0
     # ---- max over ranks ------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_pg_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms, e2e_pg_ms = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -399,24 +468,52 @@ def run_ours(a):
                 "measured_in": "eager replica of the timed region (same process, same inputs, L2 flushed)",
                 "seed_prior_launch_ms": float(np.mean(seedl)) if seedl else None,
                 "agg_share_of_step": (sum(ms for ms, _ in agg) / dev_ms) if dev_ms else None}
+    # ---- tensor-core GEMM roofline (the largest e2e GEMM of the step) and the share table ---------------------
+    roofline_gemm = None
+    if gemm:
+        (gM, gN, gK), ts = max(gemm.items(), key=lambda kv: kv[0][0] * kv[0][2] * len(kv[1]))
+        g_ms = float(np.mean(ts))
+        flops = 3 * 2.0 * gM * gN * gK                       # three bf16 products per fp32-class product
+        tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+        roofline_gemm = {"bound": "tensor", "kernel": "linear_tc_kernel (gr_linear_tc_planes, split-bf16 x3)",
+                         "shape": {"M": gM, "N": gN, "K": gK}, "achieved": flops / (g_ms * 1e-3) / 1e12,
+                         "peak": tf_peak, "unit": "TFLOP/s", "frac": flops / (g_ms * 1e-3) / 1e12 / tf_peak,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, of measured)" if "bf16_tflops" in peaks
+                         else "1590 TFLOP/s (of fallback)",
+                         "avg_launch_ms": g_ms, "launches_per_step": len(ts) // max(a.steps, 1),
+                         "fp32_equivalent_tflops": 2.0 * gM * gN * gK / (g_ms * 1e-3) / 1e12}
+    shares = {k: v / rep_ms for k, v in sorted(op_ms.items(), key=lambda kv: -kv[1])} if rep_ms else {}
+    shares["_note"] = ("device time per kernel class / eager step time, from CUDA events around every wrapper in the "
+                       "eager replica (the question side runs on a second stream and overlaps: shares can sum past 1)")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(a.config, c, {
+            "config": config_dict(a.config, c, world=world, extra={
                 "global_questions": world * B, "l2": "256 MiB flush write between timed steps",
                 "timing": "CUDA events per step on the launch stream, max over ranks",
                 "cuda_graph": bool(a.cuda_graph),
                 "wall_s_timed_region_incl_flush": wall}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "mode": e2e_mode},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "mode": e2e_mode,
+                    "from_pageable_numpy": {
+                        "value": world * B * a.steps / (e2e_pg_ms / 1e3) if e2e_pg_ms == e2e_pg_ms else None,
+                        "ms_per_step": e2e_pg_ms / a.steps if e2e_pg_ms == e2e_pg_ms else None,
+                        "h2d_bytes_per_step": int(h2d_pg),
+                        "what": "a different get_batch-layout tuple every step (pageable numpy, int64 facts, float64 "
+                                "distributions): host casts + H2D + graph + D2H inside the timed region"}},
+            "gpu_launches": int(launches), "gpu_launches_per_step": int(launches // max(a.steps, 1)), "clocks": clocks,
+            "roofline": roofline,
+            "roofline_gemm": roofline_gemm, "shares": shares}
     if not a.no_cpu_baseline and world == 1:
         sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
-        nq = min(a.cpu_sample, B)
-        qps, ms, cores = cpu_oracle_run(c, sd_cpu, nq, 3, 1)
+        nq = min(a.cpu_sample if a.cpu_sample else {"cfg3": 1, "cfg5": 1}.get(a.config, 8), B)
+        qps, ms, cores, qps_l = cpu_oracle_run(c, sd_cpu, nq, 3 if a.config not in ("cfg3", "cfg5") else 1, 1
+                                               if a.config not in ("cfg3", "cfg5") else 0)
         line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d of %d questions per forward, 3 timed forwards (oracle port of "
-                                          "the reference op sequence, torch-CPU, all host threads)" % (nq, B)}
+                                "with_get_batch": qps_l,
+                                "sample": "%d of %d questions per forward, timed forwards + ranking (oracle port of "
+                                          "the reference op sequence, torch-CPU, all host threads); with_get_batch "
+                                          "adds the reference-form batch assembly" % (nq, B)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

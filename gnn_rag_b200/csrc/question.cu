@@ -32,11 +32,17 @@ struct GemvGroup {
   float* y;
 };
 
+// y_g[n] = W_g[n, :] . x_g (+ bias_g[n]) for every group g < ng and output row n in [n0, n1) (default: all N rows);
+// four rows per warp pass, lanes across K.  The dot order of a row does not depend on the row range, so a range split
+// over several CTAs gives the bits of the unsplit call.
 template <int G>
-__device__ __forceinline__ void block_gemv(const GemvGroup (&grp)[G], int ng, int64_t ldw, int N, int K) {
+__device__ __forceinline__ void block_gemv(const GemvGroup (&grp)[G], int ng, int64_t ldw, int N, int K, int n0 = 0,
+                                           int n1 = -1) {
   constexpr int NT = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int rows = ng * N;
+  if (n1 < 0) n1 = N;
+  const int Nr = n1 - n0;
+  const int rows = ng * Nr;
   for (int m0 = warp * NT; m0 < rows; m0 += nw * NT) {
     float acc[NT];
     const float* wr[NT];
@@ -44,7 +50,7 @@ __device__ __forceinline__ void block_gemv(const GemvGroup (&grp)[G], int ng, in
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const int m = min(m0 + t, rows - 1);
-      const int g = m / N, n = m - g * N;
+      const int g = m / Nr, n = n0 + (m - g * Nr);
       acc[t] = 0.f;
       wr[t] = grp[g].W + (int64_t)n * ldw;
       xs[t] = grp[g].x;
@@ -60,7 +66,7 @@ __device__ __forceinline__ void block_gemv(const GemvGroup (&grp)[G], int ng, in
       for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
       const int m = m0 + t;
       if (lane == 0 && m < rows) {
-        const int g = m / N, n = m - g * N;
+        const int g = m / Nr, n = n0 + (m - g * Nr);
         grp[g].y[n] = acc[t] + (grp[g].bias ? grp[g].bias[n] : 0.f);
       }
     }
@@ -172,8 +178,12 @@ __global__ void __launch_bounds__(kQThreads) query_reform_kernel(const ReformPar
   __shared__ int s_list[kQThreads];
   __shared__ float s_val[kQThreads];
   __shared__ int s_woff[kQThreads / 32 + 1];
+  // grid (B, S): CTA (b, s) owns output columns [d0, d1) of question b's new instructions (the seed pick is cheap and
+  // repeated by every slice); 4 x as many CTAs as questions: the one-CTA-per-question version occupied 64 of 148 SMs
   const int D = p.D, N = p.N, b = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int dper = (D + gridDim.y - 1) / gridDim.y;
+  const int d0 = min(D, (int)blockIdx.y * dper), d1 = min(D, d0 + dper);
   float* s_y = smq;            // [D]        seed_retrieve
   float* s_z = s_y + D;        // [I][3D]
   float* s_g = s_z + (size_t)p.I * 3 * D;   // [I][D]
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(kQThreads) query_reform_kernel(const ReformPar
   }
   if (tid < D) {
     s_y[tid] = acc;
-    if (p.seed_out) p.seed_out[(int64_t)b * D + tid] = acc;
+    if (p.seed_out && blockIdx.y == 0) p.seed_out[(int64_t)b * D + tid] = acc;
   }
   __syncthreads();
   // ---- Fusion per instruction: z = [x, y, x-y]; g = sigmoid(G z); out = g * (R z) + (1-g) * x ----
@@ -226,13 +236,13 @@ __global__ void __launch_bounds__(kQThreads) query_reform_kernel(const ReformPar
       grp[2 * j] = GemvGroup{p.Wg[j], nullptr, s_z + (size_t)j * 3 * D, s_g + (size_t)j * D};
       grp[2 * j + 1] = GemvGroup{p.Wr[j], nullptr, s_z + (size_t)j * 3 * D, s_r + (size_t)j * D};
     }
-    block_gemv(grp, 2 * p.I, 3 * D, D, 3 * D);
+    block_gemv(grp, 2 * p.I, 3 * D, D, 3 * D, d0, d1);
   }
   __syncthreads();
-  for (int i = tid; i < p.I * D; i += blockDim.x) {
-    const int j = i / D, d = i - j * D;
-    const float g = 1.f / (1.f + expf(-s_g[i]));
-    p.ins_out[((int64_t)b * p.I + j) * D + d] = g * s_r[i] + (1.f - g) * s_z[(size_t)j * 3 * D + d];
+  for (int i = tid; i < p.I * (d1 - d0); i += blockDim.x) {
+    const int j = i / (d1 - d0), d = d0 + (i - j * (d1 - d0));
+    const float g = 1.f / (1.f + expf(-s_g[(size_t)j * D + d]));
+    p.ins_out[((int64_t)b * p.I + j) * D + d] = g * s_r[(size_t)j * D + d] + (1.f - g) * s_z[(size_t)j * 3 * D + d];
   }
 }
 
@@ -369,7 +379,8 @@ extern "C" int gr_query_reform(const float* seed_info, const float* h, int64_t l
   p.B = B; p.N = N; p.D = D; p.I = I;
   const size_t smem = ((size_t)1 + 5 * (size_t)I) * D * sizeof(float);
   GR_CHECK_ARG(smem <= 48 * 1024, "num_ins x entity_dim too large for shared memory");
-  query_reform_kernel<<<B, kQThreads, smem, stream>>>(p);
+  const int slices = D >= 128 ? 4 : (D >= 64 ? 2 : 1);
+  query_reform_kernel<<<dim3((unsigned)B, (unsigned)slices), kQThreads, smem, stream>>>(p);
   GR_CHECK_LAUNCH();
   return GR_OK;
 }

@@ -162,6 +162,33 @@ class BaseModel(nn.Module):
         case_valid = (torch.sum(answer_dist, dim=1, keepdim=True) > 0).float()
         return self.calc_loss_label(pred_dist, answer_dist, case_valid), torch.max(pred_dist, dim=1)[1]
 
+    FORK_QUESTION_SIDE = True
+
+    def _fork_instructions(self, q_input):
+        """Run the instruction encoder on a side stream; pair with :meth:`_join_instructions`."""
+        if not self.FORK_QUESTION_SIDE:
+            return self.instruction(q_input)
+        cur = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != cur.device:
+            side = self._side_stream = torch.cuda.Stream(device=cur.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ins = self.instruction(q_input)
+        return ins
+
+    def _join_instructions(self, ins):
+        if self.FORK_QUESTION_SIDE:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self._side_stream)
+            # tensors produced on the side stream and read on this one from now on
+            enc = self.instruction
+            for t in (ins, getattr(enc, "query_hidden_emb", None), getattr(enc, "query_node_emb", None),
+                      getattr(enc, "relational_ins", None)):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(cur)
+        return ins
+
     def _check_ready(self):
         dev = self.word_embedding.weight.device
         if dev.type != "cuda":
@@ -226,10 +253,13 @@ class ReaRev(BaseModel):
         db = batching.stage_batch(batch, dev, self.num_relation + 1, self.normalized_gnn, self.norm_rel)
         self.last_batch = db
         B, N = db.B, db.N
+        # the question side (embedding -> LSTM / LM -> instruction attention) does not depend on the graph side (relation
+        # features, hoisted tables, TypeLayer): fork it onto a second stream (captured as a parallel branch by GraphedStep)
+        instructions = self._fork_instructions(db.q_input)
         rel_f = self.get_rel_feature()                           # both directions, stacked
         self.reasoning.init_reason(db, rel_f)
         self._get_ent_init(db, rel_f, self.reasoning)           # TypeLayer straight into the h slot
-        instructions = self.instruction(db.q_input)              # rearev.py:192-196
+        instructions = self._join_instructions(instructions)     # rearev.py:192-196
         self.dist_history = [db.seed_dist]
         h = None
         reforms = [getattr(self, "reform" + str(j)).fusion for j in range(I)]
@@ -299,10 +329,11 @@ class NSM(BaseModel):
         dev = self._check_ready()
         db = batching.stage_batch(batch, dev, self.num_relation + 1, self.normalized_gnn, self.norm_rel)
         self.last_batch = db
+        instruction_list = self._fork_instructions(db.q_input)
         rel_f = self.get_rel_feature()
         self.reasoning.init_reason(db, rel_f)
         self._get_ent_init(db, rel_f, self.reasoning)
-        instruction_list = self.instruction(db.q_input)
+        instruction_list = self._join_instructions(instruction_list)
         dist = db.seed_dist
         self.dist_history = [dist]
         for i in range(self.num_step):                           # nsm.py:219-222

@@ -21,10 +21,13 @@ class _Stats:
         self.launches = 0
         self.time_agg = False
         self.agg_events = []      # (start_event, end_event, tag)
+        self.time_ops = False     # bench.py's per-kernel-class share table: events around every wrapper below
+        self.op_events = []       # (start_event, end_event, class tag, info)
 
     def reset(self):
         self.launches = 0
         self.agg_events = []
+        self.op_events = []
 
 
 STATS = _Stats()
@@ -35,16 +38,38 @@ class _AggTimer:
         self.tag = tag
 
     def __enter__(self):
-        if STATS.time_agg:
+        if STATS.time_agg or STATS.time_ops:
             self.s = torch.cuda.Event(enable_timing=True)
             self.e = torch.cuda.Event(enable_timing=True)
             self.s.record()
         return self
 
     def __exit__(self, *a):
-        if STATS.time_agg:
+        if STATS.time_agg or STATS.time_ops:
             self.e.record()
-            STATS.agg_events.append((self.s, self.e, self.tag))
+            if STATS.time_agg:
+                STATS.agg_events.append((self.s, self.e, self.tag))
+            if STATS.time_ops:
+                STATS.op_events.append((self.s, self.e, "aggregation", self.tag))
+
+
+class _OpTimer:
+    """CUDA events (on the launching stream) around one wrapper call when ``STATS.time_ops`` is on."""
+
+    def __init__(self, cls, info=None):
+        self.cls, self.info = cls, info
+
+    def __enter__(self):
+        if STATS.time_ops:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if STATS.time_ops:
+            self.e.record()
+            STATS.op_events.append((self.s, self.e, self.cls, self.info))
 
 
 def _L():
@@ -121,11 +146,12 @@ def csr_build(heads, rels, tails, B, N, R1, nfacts=None):
     L = _L()
     ws_bytes = L.gr_csr_build_workspace_bytes(F, B * N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=heads.device)
-    rc = L.gr_csr_build(_p(heads.contiguous()), _p(rels.contiguous()), _p(tails.contiguous()),
-                        heads.element_size(), F, B * N, R1,
-                        _p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(g.fact_t),
-                        _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(g.fact_h),
-                        _p(g.status), _p(nfacts), _p(ws), ws_bytes, _stream())
+    with _OpTimer("csr_build"):
+        rc = L.gr_csr_build(_p(heads.contiguous()), _p(rels.contiguous()), _p(tails.contiguous()),
+                            heads.element_size(), F, B * N, R1,
+                            _p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(g.fact_t),
+                            _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(g.fact_h),
+                            _p(g.status), _p(nfacts), _p(ws), ws_bytes, _stream())
     _lib.check(rc)
     STATS.launches += 9 if F > 0 else 5     # memsets excluded: hist, 3x scan, place, 2x sort, fill (+gather)
     return g
@@ -256,7 +282,8 @@ def pad_table256(table):
     rows, D = table.shape
     assert table.stride(1) == 1
     pn = torch.empty(rows, 256, dtype=torch.float32, device=table.device)
-    _lib.check(_L().gr_pad_table256(_p(table), table.stride(0), rows, D, _p(pn), _stream()))
+    with _OpTimer("table_prep"):
+        _lib.check(_L().gr_pad_table256(_p(table), table.stride(0), rows, D, _p(pn), _stream()))
     STATS.launches += 1
     return pn
 
@@ -295,10 +322,11 @@ def type_layer(g, table, out, w_t=None, w_h=None, planes=None):
     D = table.shape[1]
     assert out is None or out.stride(1) == 1
     hi, lo = planes if planes is not None else (None, None)
-    rc = _L().gr_type_layer(_p(g.rowptr_t), _p(g.rel_t), _p(w_t), _p(g.rowptr_h), _p(g.rel_h), _p(w_h),
-                            _p(table), _p(out), out.stride(0) if out is not None else 0,
-                            _p(hi), _p(lo), hi.stride(0) if hi is not None else 0,
-                            g.B, g.N, D, g.F, _stream())
+    with _OpTimer("type_layer"):
+        rc = _L().gr_type_layer(_p(g.rowptr_t), _p(g.rel_t), _p(w_t), _p(g.rowptr_h), _p(g.rel_h), _p(w_h),
+                                _p(table), _p(out), out.stride(0) if out is not None else 0,
+                                _p(hi), _p(lo), hi.stride(0) if hi is not None else 0,
+                                g.B, g.N, D, g.F, _stream())
     _lib.check(rc)
     STATS.launches += 1
     return out
@@ -396,11 +424,12 @@ def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=
     ws, presplit = _weight_ws(W, N, K, k_seg, k_seg_pitch, nbytes)
     chi, clo = out_planes if out_planes is not None else (None, None)
     flags = (LINEAR_RELU if relu else 0) | (LINEAR_W_PRESPLIT if presplit else 0)
-    rc = L.gr_linear_tc_planes(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(W), W.stride(0), _p(bias),
-                               _p(out), out.stride(0) if out is not None else 0,
-                               _p(chi), _p(clo), chi.stride(0) if chi is not None else 0,
-                               _p(w_score), _p(dots), M, N, K, k_seg, k_seg_pitch,
-                               flags, _p(ws), nbytes, _stream())
+    with _OpTimer("gemm_tc", (M, N, K)):
+        rc = L.gr_linear_tc_planes(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(W), W.stride(0), _p(bias),
+                                   _p(out), out.stride(0) if out is not None else 0,
+                                   _p(chi), _p(clo), chi.stride(0) if chi is not None else 0,
+                                   _p(w_score), _p(dots), M, N, K, k_seg, k_seg_pitch,
+                                   flags, _p(ws), nbytes, _stream())
     _lib.check(rc)
     STATS.launches += 1 if presplit else 2
     return out
@@ -487,8 +516,9 @@ SPARSE_PRIOR_FASTPATH = True   # first layer of every ReaRev iteration (seed pri
 def frontier_rows(g, prior, rows, count):
     """rows/count <- destination rows with at least one in-edge (either direction) from a node with prior != 0."""
     prior = _cuda(prior, torch.float32, "prior").contiguous()
-    _lib.check(_L().gr_frontier_rows(_p(g.rowptr_t), _p(g.src_t), _p(g.rowptr_h), _p(g.src_h), _p(prior),
-                                     g.B * g.N, _p(rows), _p(count), _stream()))
+    with _OpTimer("frontier"):
+        _lib.check(_L().gr_frontier_rows(_p(g.rowptr_t), _p(g.src_t), _p(g.rowptr_h), _p(g.src_h), _p(prior),
+                                         g.B * g.N, _p(rows), _p(count), _stream()))
     STATS.launches += 1
 
 
@@ -501,11 +531,12 @@ def frontier_fixup(g, prior, table_fwd, table_inv, ins, cur_planes, W, bias, w_s
     chi, clo = cur_planes
     nhi, nlo = nxt_planes
     assert W.stride(1) == 1 and table_fwd.is_contiguous() and table_inv.is_contiguous()
-    rc = _L().gr_frontier_fixup(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t), _p(g.rowptr_h), _p(g.src_h),
-                                _p(g.rel_h), _p(w_h), _p(prior), _p(table_fwd), _p(table_inv), _p(ins),
-                                _p(chi), _p(clo), chi.stride(0), _p(W), W.stride(0), _p(bias), _p(w_score),
-                                _p(nhi), _p(nlo), nhi.stride(0), _p(h32), _p(dots), _p(rows), _p(count),
-                                B, g.N, D, I, _stream())
+    with _OpTimer("frontier"):
+        rc = _L().gr_frontier_fixup(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t), _p(g.rowptr_h), _p(g.src_h),
+                                    _p(g.rel_h), _p(w_h), _p(prior), _p(table_fwd), _p(table_inv), _p(ins),
+                                    _p(chi), _p(clo), chi.stride(0), _p(W), W.stride(0), _p(bias), _p(w_score),
+                                    _p(nhi), _p(nlo), nhi.stride(0), _p(h32), _p(dots), _p(rows), _p(count),
+                                    B, g.N, D, I, _stream())
     _lib.check(rc)
     STATS.launches += 1
 
@@ -515,8 +546,9 @@ def masked_softmax(dots, b_score, mask, B, N):
     ``dots`` = the [2, B*N] partial score dots of :func:`linear_tc_planes`."""
     dist = torch.empty(B, N, dtype=torch.float32, device=dots.device)
     d = dots.view(2, -1)
-    _lib.check(_L().gr_masked_softmax(_p(d[0]), _p(d[1]), _p(b_score), _p(mask.contiguous()), _p(dist), B, N,
-                                      _stream()))
+    with _OpTimer("softmax"):
+        _lib.check(_L().gr_masked_softmax(_p(d[0]), _p(d[1]), _p(b_score), _p(mask.contiguous()), _p(dist), B, N,
+                                          _stream()))
     STATS.launches += 1
     return dist
 
@@ -560,9 +592,10 @@ def instructions(hidden, qnode, qtext, pad_id, Wq, bq, Wcq, bcq, wca, bca):
     B, Q, D = hidden.shape
     I = len(Wq)
     out = torch.empty(B, I, D, dtype=torch.float32, device=hidden.device)
-    rc = _L().gr_instructions(_p(hidden), _p(qnode), _p(qtext), int(pad_id), _ptr_array(Wq), _ptr_array(bq),
-                              _p(Wcq.contiguous()), _p(bcq), _p(wca.contiguous()), _p(bca), _p(out), None,
-                              B, Q, D, I, _stream())
+    with _OpTimer("question_side"):
+        rc = _L().gr_instructions(_p(hidden), _p(qnode), _p(qtext), int(pad_id), _ptr_array(Wq), _ptr_array(bq),
+                                  _p(Wcq.contiguous()), _p(bcq), _p(wca.contiguous()), _p(bca), _p(out), None,
+                                  B, Q, D, I, _stream())
     _lib.check(rc)
     STATS.launches += 1
     return out
@@ -579,7 +612,8 @@ def lstm_forward(gates_x, W_hh, b_hh):
     D = G // 4
     assert W_hh.shape == (4 * D, D) and W_hh.is_contiguous()
     hidden = torch.empty(B, Q, D, dtype=torch.float32, device=gates_x.device)
-    _lib.check(_L().gr_lstm_forward(_p(gates_x), _p(W_hh), _p(b_hh), _p(hidden), B, Q, D, _stream()))
+    with _OpTimer("question_side"):
+        _lib.check(_L().gr_lstm_forward(_p(gates_x), _p(W_hh), _p(b_hh), _p(hidden), B, Q, D, _stream()))
     STATS.launches += 1
     return hidden
 
@@ -592,8 +626,9 @@ def query_reform(seed_info, h, ins, Wr, Wg, B, N):
     assert h.stride(1) == 1
     _, I, D = ins.shape
     out = torch.empty_like(ins)
-    rc = _L().gr_query_reform(_p(seed_info), _p(h), h.stride(0), _p(ins), _ptr_array(Wr), _ptr_array(Wg),
-                              _p(out), None, B, N, D, I, _stream())
+    with _OpTimer("query_reform"):
+        rc = _L().gr_query_reform(_p(seed_info), _p(h), h.stride(0), _p(ins), _ptr_array(Wr), _ptr_array(Wg),
+                                  _p(out), None, B, N, D, I, _stream())
     _lib.check(rc)
     STATS.launches += 1
     return out
@@ -607,7 +642,8 @@ def kl_loss_pred(dist, teacher):
     loss_q = torch.empty(B, dtype=torch.float32, device=dist.device)
     loss = torch.empty((), dtype=torch.float32, device=dist.device)
     pred = torch.empty(B, dtype=torch.int64, device=dist.device)
-    _lib.check(_L().gr_kl_loss_pred(_p(dist), _p(teacher), _p(loss_q), _p(loss), _p(pred), B, N, _stream()))
+    with _OpTimer("loss_rank"):
+        _lib.check(_L().gr_kl_loss_pred(_p(dist), _p(teacher), _p(loss_q), _p(loss), _p(pred), B, N, _stream()))
     STATS.launches += 2
     return loss, pred
 
@@ -625,9 +661,10 @@ def rank_candidates(dist, local_entity, query_entities, pad_id, eps):
     L = _L()
     nbytes = L.gr_rank_workspace_bytes(B, N)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    rc = L.gr_rank_candidates(_p(dist), _p(local_entity), _p(query_entities), int(pad_id), float(eps),
-                              _p(cand_idx), _p(cand_count), _p(cand_total), B, N, _p(ws), nbytes,
-                              _stream())
+    with _OpTimer("loss_rank"):
+        rc = L.gr_rank_candidates(_p(dist), _p(local_entity), _p(query_entities), int(pad_id), float(eps),
+                                  _p(cand_idx), _p(cand_count), _p(cand_total), B, N, _p(ws), nbytes,
+                                  _stream())
     _lib.check(rc)
     STATS.launches += 1
     return cand_idx, cand_count, cand_total

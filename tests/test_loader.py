@@ -43,6 +43,29 @@ def test_build_fact_mat_matches_reference_golden(name):
     assert np.random.rand() == expect_next
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_loader_oracle_matches_reference_golden(name):
+    """oracle/loader_oracle.py (the reference-form restatement bench.py times as the CPU get_batch cost) against the
+    arrays recorded from the unmodified reference."""
+    from oracle import loader_oracle
+    kw, ids, dropout, seed = CASES[name]
+    gold = np.load(os.path.join(GOLD, "fact_mat_%s.npz" % name))
+    np.random.seed(seed)
+    got = loader_oracle.build_fact_mat(FakeLoader(**kw), ids, dropout)
+    assert_same(got, [gold[k] for k in KEYS])
+
+
+def test_loader_oracle_state_from_synthetic_batch_round_trip():
+    from gnn_rag_b200 import synthetic as S
+    from oracle import loader_oracle
+    b = S.make_batch(5, B=4, N=30, E=90, num_entity=500, num_relation=12, num_word=50, n_real="ragged")
+    st = loader_oracle.state_from_batch(b, 12)
+    np.random.seed(0)
+    got = loader_oracle.build_fact_mat(st, list(range(4)), 0.0)
+    key = lambda h, r, t: sorted(zip(h.tolist(), r.tolist(), t.tolist()))          # same multiset of facts
+    assert key(got[0], got[1], got[2]) == key(b[2][0], b[2][1], b[2][2])
+
+
 def test_variants_and_install():
     kw, ids, dropout, seed = CASES["small"]
     ld = FakeLoader(**kw)
