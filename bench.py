@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--agg-abs-ws", type=int, default=None, help="0: one CTA per tile instead of the persistent kernel")
     ap.add_argument("--tc-bk", type=int, default=None)
     ap.add_argument("--tc-cluster", type=int, default=None)
+    ap.add_argument("--act-bf16", type=int, default=None,
+                    help="1: bf16 activation storage (hi plane only, one-product GEMM); default: on for cfg3 "
+                         "(BASELINE configs[2] names bf16), off elsewhere")
     ap.add_argument("--cuda-graph", type=int, default=1,
                     help="1: run the step through gnn_rag_b200.GraphedStep (CUDA-graph replay over static buffers)")
     return ap.parse_args()
@@ -225,12 +228,14 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def agg_algorithmic_bytes(B, N, F, D, I, R1):
+def agg_algorithmic_bytes(B, N, F, D, I, R1, out_elem_bytes=4):
     """Minimal HBM bytes of ONE fused aggregation launch (both directions, I instructions), fp32/int32:
-    two CSRs (src+rel per edge, row pointers), prior, two relation tables, instructions, 2*I output rows.
+    two CSRs (src+rel per edge, row pointers), prior, two relation tables, instructions, 2*I output rows
+    (4 bytes per element as split-bf16 hi+lo, 2 with bf16 activation storage).
     (= 2*I units of SURVEY.md 8d minus the reads the fused launch shares.)"""
     Nt = B * N
-    return 2 * F * 8 + 2 * (Nt + 1) * 4 + Nt * 4 + 2 * R1 * D * 4 + B * I * D * 4 + 2 * I * Nt * D * 4
+    return (2 * F * 8 + 2 * (Nt + 1) * 4 + Nt * 4 + 2 * R1 * D * 4 + B * I * D * 4
+            + 2 * I * Nt * D * out_elem_bytes)
 
 
 def run_ours(a):
@@ -258,6 +263,8 @@ def run_ours(a):
         ops.set_option("tc_bk", a.tc_bk)
     if a.tc_cluster is not None:
         ops.set_option("tc_cluster", a.tc_cluster)
+    act_bf16 = bool(a.act_bf16) if a.act_bf16 is not None else (a.config == "cfg3")
+    ops.ACT_BF16 = act_bf16
     c = per_gpu_config(a.config)
     B, N, D, I = c["B"], c["N"], c["D"], c["I"]
     args = model_args_for(c, True)
@@ -448,7 +455,7 @@ def run_ours(a):
     else:
         dense = [ms for i, (ms, _) in enumerate(agg) if (i % per_step) % K != 0] if per_step else []
         seedl = [ms for i, (ms, _) in enumerate(agg) if (i % per_step) % K == 0] if per_step else []
-    abytes = agg_algorithmic_bytes(B, N, F, D, I, R1)
+    abytes = agg_algorithmic_bytes(B, N, F, D, I, R1, 2 if act_bf16 else 4)
     traffic = None     # dram__bytes_read+write of the dense-prior launch from the committed ncu --set full capture
     try:
         import glob
@@ -473,9 +480,11 @@ def run_ours(a):
     if gemm:
         (gM, gN, gK), ts = max(gemm.items(), key=lambda kv: kv[0][0] * kv[0][2] * len(kv[1]))
         g_ms = float(np.mean(ts))
-        flops = 3 * 2.0 * gM * gN * gK                       # three bf16 products per fp32-class product
+        nprod = 1 if act_bf16 else 3                         # bf16 products per output (3 = fp32-class split)
+        flops = nprod * 2.0 * gM * gN * gK
         tf_peak = float(peaks.get("bf16_tflops", 1590.0))
-        roofline_gemm = {"bound": "tensor", "kernel": "linear_tc_kernel (gr_linear_tc_planes, split-bf16 x3)",
+        roofline_gemm = {"bound": "tensor", "kernel": "linear_tc_kernel (gr_linear_tc_planes, %d bf16 product%s)" % (
+                             nprod, "s" if nprod > 1 else ""),
                          "shape": {"M": gM, "N": gN, "K": gK}, "achieved": flops / (g_ms * 1e-3) / 1e12,
                          "peak": tf_peak, "unit": "TFLOP/s", "frac": flops / (g_ms * 1e-3) / 1e12 / tf_peak,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, of measured)" if "bf16_tflops" in peaks
@@ -487,7 +496,9 @@ def run_ours(a):
                        "eager replica (the question side runs on a second stream and overlaps: shares can sum past 1)")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 activation storage, f32 tables / accumulate / scores" if act_bf16 else "f32",
+            "data": "synthetic",
             "config": config_dict(a.config, c, world=world, extra={
                 "global_questions": world * B, "l2": "256 MiB flush write between timed steps",
                 "timing": "CUDA events per step on the launch stream, max over ranks",

@@ -90,6 +90,7 @@ __device__ __forceinline__ float4 addsub4(const float4& q, const float4& s, floa
 }
 
 // y = xp*(Q+S) + xn*(Q-S)  (xp, xn already carry the 1/2) -> (hi, lo) bf16 pairs, 8-byte stores into both planes
+template <bool LO = true>
 __device__ __forceinline__ void emit4(__nv_bfloat16* ph, __nv_bfloat16* pl, bool pred, const float4& xp,
                                       const float4& xn, const float4& U, const float4& V) {
   float2 y01 = __fmul2_rn(make_float2(xp.x, xp.y), make_float2(U.x, U.y));
@@ -101,6 +102,10 @@ __device__ __forceinline__ void emit4(__nv_bfloat16* ph, __nv_bfloat16* pl, bool
   const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
   const float2 f01 = make_float2(__uint_as_float(u01 << 16), __uint_as_float(u01 & 0xffff0000u));
   const float2 f23 = make_float2(__uint_as_float(u23 << 16), __uint_as_float(u23 & 0xffff0000u));
+  if (!LO) {                                    // bf16 activation storage: the hi plane only
+    if (pred) *reinterpret_cast<uint2*>(ph) = make_uint2(u01, u23);
+    return;
+  }
   const float2 m1 = make_float2(-1.f, -1.f);
   const float2 r01 = __ffma2_rn(f01, m1, y01), r23 = __ffma2_rn(f23, m1, y23);   // y - hi, exact, packed
   const __nv_bfloat162 l01 = __floats2bfloat162_rn(r01.x, r01.y);
@@ -130,7 +135,7 @@ struct LaneIns {
 
 // One (destination row, direction) unit: gather + accumulate the row's in-edges, then emit the NI instruction
 // segments.  rc: staged {table byte offset, coefficient} of the tile's edge slice; [beg, end) the row's range in it.
-template <int NI, int DT, int SEGP>
+template <int NI, int DT, int SEGP, bool LO = true>
 __device__ __forceinline__ void row_unit(const int2* __restrict__ rc, int beg, int end, int ebase, const PnDir& dd,
                                          const float* __restrict__ prior, const char* tb, const LaneIns<NI>& x,
                                          __nv_bfloat16* hrow, __nv_bfloat16* lrow, int seg_d, bool ld1, bool wr1) {
@@ -170,8 +175,8 @@ __device__ __forceinline__ void row_unit(const int2* __restrict__ rc, int beg, i
 #pragma unroll
   for (int j = 0; j < NI; ++j) {
     const int seg = seg_d + j * 2 * SEGP;
-    emit4(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
-    emit4(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
+    emit4<LO>(hrow + seg, lrow + seg, true, x.xp[j][0], x.xn[j][0], U0, V0);
+    emit4<LO>(hrow + seg + 128, lrow + seg + 128, wr1, x.xp[j][1], x.xn[j][1], U1, V1);
   }
 }
 
@@ -397,7 +402,7 @@ __device__ __forceinline__ void produce_tile_rows(Buf& bf, const PnParams& p, in
 // against 131 us for 8 + 1 / 64 rows).  More warps do not help: 11 + 1 at 80 registers 143 us, 19 + 1 in one CTA
 // 164 us, 7 + 1 x 3 CTAs 148 us (profiles/r2_agg_modes.txt).
 // ---------------------------------------------------------------------------------------------------------
-template <int NI, int DT, int SEGP, int KW, int ROWS, int MINB>
+template <int NI, int DT, int SEGP, int KW, int ROWS, int MINB, bool LO>
 __global__ void __launch_bounds__((KW + 1) * 32, MINB) agg_abs_wsg_kernel(const PnParams p, int ntiles) {
   using Buf = HBuf<NI, ROWS>;
   extern __shared__ __align__(16) unsigned char ws_smem[];
@@ -460,7 +465,8 @@ __global__ void __launch_bounds__((KW + 1) * 32, MINB) agg_abs_wsg_kernel(const 
       for (int d = 0; d < 2; ++d) {
         const int ebase = bf.rowptr[d][0];
         const int beg = bf.rowptr[d][lr] - ebase, end = bf.rowptr[d][lr + 1] - ebase;
-        row_unit<NI, DT, SEGP>(bf.rc[d], beg, end, ebase, p.dir[d], p.prior, tb[d], x, hrow, lrow, d * SEGP, ld1, wr1);
+        row_unit<NI, DT, SEGP, LO>(bf.rc[d], beg, end, ebase, p.dir[d], p.prior, tb[d], x, hrow, lrow, d * SEGP, ld1,
+                                   wr1);
       }
     }
     mbar_arrive(&s_empty[it & 1]);
@@ -763,9 +769,9 @@ int set_smem_once(K kern, size_t smem, bool (&done)[64]) {
   return GR_OK;
 }
 
-template <int NI, int KW, int ROWS, int MINB>
-int launch_wsg(const PnParams& p, cudaStream_t stream) {
-  auto kern = agg_abs_wsg_kernel<NI, 200, 208, KW, ROWS, MINB>;
+template <int NI, int KW, int ROWS, int MINB, bool LO>
+int launch_wsg_lo(const PnParams& p, cudaStream_t stream) {
+  auto kern = agg_abs_wsg_kernel<NI, 200, 208, KW, ROWS, MINB, LO>;
   const size_t smem = 2 * sizeof(HBuf<NI, ROWS>);
   static bool done[64] = {};
   int rc = set_smem_once(kern, smem, done);
@@ -776,6 +782,12 @@ int launch_wsg(const PnParams& p, cudaStream_t stream) {
   kern<<<pgrid, (KW + 1) * 32, smem, stream>>>(p, (int)tiles);
   GR_CHECK_LAUNCH();
   return GR_OK;
+}
+
+template <int NI, int KW, int ROWS, int MINB>
+int launch_wsg(const PnParams& p, cudaStream_t stream) {
+  // out_lo == NULL: bf16 activation storage (hi plane only)
+  return p.out_lo ? launch_wsg_lo<NI, KW, ROWS, MINB, true>(p, stream) : launch_wsg_lo<NI, KW, ROWS, MINB, false>(p, stream);
 }
 
 template <int NI, int KW, int RPW>
@@ -804,7 +816,7 @@ template <int NI>
 int launch_pn(const PnParams& p, cudaStream_t stream) {
   if (p.tile_counter && g_opt_agg_abs_ws) {
     if constexpr (NI == 2) {
-      if (g_opt_agg_abs_ws == 3 && p.table_rows > 0) return launch_g4<2, 14, 4>(p, stream);
+      if (g_opt_agg_abs_ws == 3 && p.table_rows > 0 && p.out_lo) return launch_g4<2, 14, 4>(p, stream);
     }
     if (g_opt_agg_abs_ws == 1 || p.N < 72) return launch_wsg<NI, 8, 64, 2>(p, stream);   // a tile spans <= 2 questions
     return launch_wsg<NI, 9, 72, 2>(p, stream);
@@ -842,13 +854,14 @@ extern "C" int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src
                                     int N, int D, int I, int64_t F, int32_t* tile_counter, void* stream_) {
   using namespace gr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  GR_CHECK_ARG(rowptr_t && rowptr_h && prior && pn_fwd && pn_inv && ins && out_hi && out_lo, "null pointer");
+  GR_CHECK_ARG(rowptr_t && rowptr_h && prior && pn_fwd && pn_inv && ins && out_hi, "null pointer");
+  GR_CHECK_ARG(out_lo || tile_counter, "hi-only output (bf16 activation storage) needs the persistent kernel");
   GR_CHECK_ARG(F == 0 || (src_t && rel_t && src_h && rel_h), "null edge arrays");
   GR_CHECK_ARG(B > 0 && N >= kRows && I > 0, "B, I must be positive and N >= 64");
   GR_CHECK_ARG(D == 200 && seg_pitch == 208, "this build specialises D = 200, seg_pitch = 208 (use gr_aggregate_dual)");
   GR_CHECK_ARG(ld_planes % 4 == 0 && out_col0 % 4 == 0 && ld_planes >= out_col0 + 2 * (int64_t)I * seg_pitch,
                "plane row pitch / column offset must be multiples of 4 and cover all segments");
-  GR_CHECK_ARG((reinterpret_cast<uintptr_t>(out_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(out_lo) & 7) == 0 &&
+  GR_CHECK_ARG((reinterpret_cast<uintptr_t>(out_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(out_lo) & 7) == 0 &&   /* NULL ok */
                    (reinterpret_cast<uintptr_t>(pn_fwd) & 15) == 0 && (reinterpret_cast<uintptr_t>(pn_inv) & 15) == 0,
                "misaligned planes / padded tables");
   PnParams p{};

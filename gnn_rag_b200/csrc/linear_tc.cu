@@ -283,7 +283,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int a_bytes = BM * BK * 2;            // 16384
   const int w_bytes = p.n_pad * BK * 2;       // n_pad * 128
-  const int stage_bytes = 2 * a_bytes + 2 * w_bytes;
+  // GR_LINEAR_BF16_SINGLE: bf16 activation storage -- one product A_hi W_hi, stages hold {A_hi, W_hi} only
+  const bool single = (p.flags & GR_LINEAR_BF16_SINGLE) != 0;
+  const int w_off = single ? a_bytes : 2 * a_bytes;          // W_hi tile inside a stage
+  const int stage_bytes = single ? a_bytes + w_bytes : 2 * a_bytes + 2 * w_bytes;
   // epilogue staging (TMA-store source, must be 128-byte aligned): right after the 1024-aligned stages
   uint8_t* s_out = smem + (size_t)p.stages * stage_bytes;    // [2 halves] x {fp32 128x16, hi 128x16, lo 128x16}
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 2 * kStageOutBytes);
@@ -343,15 +346,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           uint8_t* st = smem + (size_t)s * stage_bytes;
           mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m0);
-          tma_load_2d(st + a_bytes, &map_a_lo, &full_bar[s], kb * BK, m0);
+          if (!single) tma_load_2d(st + a_bytes, &map_a_lo, &full_bar[s], kb * BK, m0);
           if (CS == 1) {
-            tma_load_2d(st + 2 * a_bytes, &map_w_hi, &full_bar[s], kb * BK, 0);
-            tma_load_2d(st + 2 * a_bytes + w_bytes, &map_w_lo, &full_bar[s], kb * BK, 0);
+            tma_load_2d(st + w_off, &map_w_hi, &full_bar[s], kb * BK, 0);
+            if (!single) tma_load_2d(st + w_off + w_bytes, &map_w_lo, &full_bar[s], kb * BK, 0);
           } else {
-            tma_load_2d_mc(st + 2 * a_bytes + crank * w_slice, &map_w_hi, &full_bar[s], kb * BK,
+            tma_load_2d_mc(st + w_off + crank * w_slice, &map_w_hi, &full_bar[s], kb * BK,
                            crank * w_rows, kMask);
-            tma_load_2d_mc(st + 2 * a_bytes + w_bytes + crank * w_slice, &map_w_lo, &full_bar[s], kb * BK,
-                           crank * w_rows, kMask);
+            if (!single)
+              tma_load_2d_mc(st + w_off + w_bytes + crank * w_slice, &map_w_lo, &full_bar[s], kb * BK,
+                             crank * w_rows, kMask);
           }
           if (++s == p.stages) { s = 0; phase ^= 1; }
         }
@@ -375,14 +379,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint64_t da_hi = make_smem_desc<BK>(sa), da_lo = make_smem_desc<BK>(sa + a_bytes);
-          const uint64_t dw_hi = make_smem_desc<BK>(sa + 2 * a_bytes);
-          const uint64_t dw_lo = make_smem_desc<BK>(sa + 2 * a_bytes + w_bytes);
+          const uint64_t dw_hi = make_smem_desc<BK>(sa + w_off);
+          const uint64_t dw_lo = make_smem_desc<BK>(sa + w_off + w_bytes);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
             umma_bf16(tmem_d, da_hi + adv, dw_hi + adv, idesc, (kb | k) ? 1u : 0u);
-            umma_bf16(tmem_d, da_hi + adv, dw_lo + adv, idesc, 1u);
-            umma_bf16(tmem_d, da_lo + adv, dw_hi + adv, idesc, 1u);
+            if (!single) {
+              umma_bf16(tmem_d, da_hi + adv, dw_lo + adv, idesc, 1u);
+              umma_bf16(tmem_d, da_lo + adv, dw_hi + adv, idesc, 1u);
+            }
           }
           // free this smem stage (in every CTA of the cluster: their producers multicast into it)
           if (CS == 1) umma_commit(&empty_bar[s]); else umma_commit_mc(&empty_bar[s], kMask);
@@ -566,13 +572,13 @@ struct TcPlan {
   bool ok;
 };
 
-TcPlan plan_tc(int64_t M, int64_t N, int64_t K) {
+TcPlan plan_tc(int64_t M, int64_t N, int64_t K, bool single = false) {
   TcPlan t{};
   const int BK = g_tc_bk == 64 ? 64 : 32;
   t.ok = (N >= 8 && N <= 256 && K >= 8 && M >= 1);
   t.kp = (K + 7) / 8 * 8;
   t.n_pad = (int)((N + 15) / 16 * 16);
-  const size_t stage = 2 * (size_t)BM * BK * 2 + 2 * (size_t)t.n_pad * BK * 2;
+  const size_t stage = (single ? 1 : 2) * ((size_t)BM * BK * 2 + (size_t)t.n_pad * BK * 2);
   // 227 KB usable smem minus alignment slack, bias/score arrays, barriers and the epilogue staging buffers
   int stages = (int)((227 * 1024 - 1024 - 2048 - 256 - 2 * kStageOutBytes) / stage);
   t.stages = stages > 8 ? 8 : stages;
@@ -731,7 +737,7 @@ extern "C" int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t l
                                    void* workspace, size_t workspace_bytes, void* stream_) {
   using namespace gr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  GR_CHECK_ARG(A_hi && A_lo && W && workspace, "null pointer");
+  GR_CHECK_ARG(A_hi && (A_lo || (flags & GR_LINEAR_BF16_SINGLE)) && W && workspace, "null pointer");
   GR_CHECK_ARG(C || C_hi, "no output requested");
   GR_CHECK_ARG(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
   const bool segmented = k_seg > 0 && k_seg_pitch > k_seg;
@@ -742,7 +748,7 @@ extern "C" int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t l
   GR_CHECK_ARG(!C_hi || (C_lo && ldc16 >= N), "C_lo missing or ldc16 smaller than N");
   GR_CHECK_ARG(!dots || w_score, "dots requested without w_score");
   GR_CHECK_ARG(M < (int64_t)0x7fffffff - BM, "M exceeds int32 range");
-  TcPlan t = plan_tc(M, N, K);
+  TcPlan t = plan_tc(M, N, K, (flags & GR_LINEAR_BF16_SINGLE) != 0);
   if (!t.ok) {
     set_error("gr_linear_tc_planes: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N,
               (long long)K);
@@ -772,6 +778,6 @@ extern "C" int gr_linear_tc_planes(const void* A_hi, const void* A_lo, int64_t l
   p.c_hi = reinterpret_cast<__nv_bfloat16*>(C_hi); p.c_lo = reinterpret_cast<__nv_bfloat16*>(C_lo);
   p.ldc16 = ldc16; p.w_score = w_score; p.dots = dots;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.flags = flags;
-  return launch_tc(reinterpret_cast<const __nv_bfloat16*>(A_hi), reinterpret_cast<const __nv_bfloat16*>(A_lo),
-                   lda16, w_hi, w_lo, t.kp, t, p, stream);
+  return launch_tc(reinterpret_cast<const __nv_bfloat16*>(A_hi),
+                   reinterpret_cast<const __nv_bfloat16*>(A_lo ? A_lo : A_hi), lda16, w_hi, w_lo, t.kp, t, p, stream);
 }

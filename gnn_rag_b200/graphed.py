@@ -130,6 +130,31 @@ class GraphedStep:
                            + 3 * F * idx_b + 4 + 4 * F * (int(st.weight_list is not None) +
                                                           int(st.weight_rel_list is not None)))
 
+    @staticmethod
+    def _needs_staging(batch):
+        """True when the batch lives in pageable host memory (numpy arrays / unpinned CPU tensors)."""
+        x = batch[2][0]
+        if isinstance(x, torch.Tensor):
+            return (not x.is_cuda) and (not x.is_pinned())
+        return True
+
+    def _stage_host(self, stage, batch):
+        """Cast + copy a pageable ``get_batch`` tuple into the pinned staging set (host memcpy); returns a tuple over the
+        staged tensors that ``_fill`` can DMA asynchronously."""
+        le, qe, kb, qi, sd, _, ad = batch[:7]
+        F = int(kb[0].shape[0])
+
+        def put(dst, src, n=None):
+            d = dst.numpy() if n is None else dst.numpy()[:n]
+            np.copyto(d, src.numpy() if isinstance(src, torch.Tensor) else np.asarray(src), casting="unsafe")
+            return dst if n is None else dst[:n]
+        wl = put(stage.weight_list, np.asarray(kb[5], dtype=np.float32), F) if stage.weight_list is not None else None
+        wr = put(stage.weight_rel_list, np.asarray(kb[6], dtype=np.float32), F) if stage.weight_rel_list is not None \
+            else None
+        kb2 = (put(stage.heads, kb[0], F), put(stage.rels, kb[1], F), put(stage.tails, kb[2], F), None, None, wl, wr)
+        return (put(stage.local_entity, le), put(stage.query_entities, qe), kb2, put(stage.q_input, qi),
+                put(stage.seed_dist, sd), None, put(stage.answer_dist, ad))
+
     def _entry(self, batch):
         le, kb, qi = batch[0], batch[2], batch[3]
         B, N = le.shape
@@ -208,6 +233,18 @@ class GraphedStep:
                                       for k, v in od.items()})
                 pipe.land_free.append(None)
                 pipe.done.append(None)
+                # pinned host staging of the inputs: pageable loader output (numpy, int64 / float64) is cast and copied
+                # here by the host (memcpy speed), the DMA to the landing set then runs asynchronously
+                stage = _Captured()
+                for name in self._names():
+                    t = getattr(ent.st, name)
+                    setattr(stage, name, torch.empty(t.shape, dtype=t.dtype, pin_memory=True))
+                stage.weight_list = getattr(stage, "weight_list", None)
+                stage.weight_rel_list = getattr(stage, "weight_rel_list", None)
+                pipe.stage = getattr(pipe, "stage", [])
+                pipe.stage.append(stage)
+                pipe.h2d_done = getattr(pipe, "h2d_done", [])
+                pipe.h2d_done.append(None)
             ent.pipe = pipe
         return ent.pipe
 
@@ -223,10 +260,16 @@ class GraphedStep:
         if pipe.land_free[slot] is not None:
             cs.wait_event(pipe.land_free[slot])
         land = pipe.land[slot]
+        src = batch
+        if self._needs_staging(batch):
+            if pipe.h2d_done[slot] is not None:
+                pipe.h2d_done[slot].synchronize()    # the previous DMA out of this staging set has finished
+            src = self._stage_host(pipe.stage[slot], batch)
         with torch.cuda.stream(cs):
-            self._fill(land, batch)
+            self._fill(land, src)
             h2d_done = torch.cuda.Event()
             h2d_done.record(cs)
+        pipe.h2d_done[slot] = h2d_done
         cur.wait_event(h2d_done)
         for name in self._names():                   # landing set -> the graph's static inputs (D2D, ~10 us)
             getattr(ent.st, name).copy_(getattr(land, name), non_blocking=True)

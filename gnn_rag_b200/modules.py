@@ -283,7 +283,7 @@ class _GraphLayerBase(nn.Module):
 
     def _alloc(self, Nt, Kd, device):
         D = self.entity_dim
-        self.use_planes = bool(ops.TC_LINEAR) and 8 <= D <= 256
+        self.use_planes = bool(ops.TC_LINEAR) and 8 <= D <= ops.TC_MAX_N_SPLIT
         self.cur = 0
         self.Kd = Kd
         if self.use_planes:
@@ -334,7 +334,7 @@ class _GraphLayerBase(nn.Module):
             nhi, nlo = self.P[1 - self.cur]
             ops.linear_tc_planes(hi, lo, self.Kpad, e2e.weight, e2e.bias, out=self.h32 if need_h32 else None,
                                  out_planes=(nhi, nlo), w_score=sw, dots=self.dots, relu=True, k_seg=D,
-                                 k_seg_pitch=self.Dp)
+                                 k_seg_pitch=self.Dp, single_ok=True)
             self.h32_valid = bool(need_h32)
             self.cur = 1 - self.cur
             return ops.masked_softmax(self.dots, sb, mask, self.B, self.N)

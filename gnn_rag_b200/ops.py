@@ -11,6 +11,12 @@ from . import _lib
 LINEAR_RELU = 1
 LINEAR_EXACT_FP32 = 2
 LINEAR_W_PRESPLIT = 4
+LINEAR_BF16_SINGLE = 8
+
+# bf16 ACTIVATION STORAGE (BASELINE configs[2], "bf16"): the layer-input matrix keeps its hi plane only -- the aggregation
+# kernel skips the lo plane (half the output bytes) and the e2e GEMM runs ONE bf16 product instead of three.  Tables,
+# accumulation, scores and softmax stay fp32.  Off by default (cfg2's contract is fp32); bench.py --config cfg3 turns it on.
+ACT_BF16 = False
 
 
 class _Stats:
@@ -302,6 +308,8 @@ def aggregate_dual_abs(g, prior, pn_fwd, pn_inv, ins, planes, out_col0, seg_pitc
     B, I, D = ins.shape
     hi, lo = planes
     assert pn_fwd.is_contiguous() and pn_inv.is_contiguous() and hi.stride(0) == lo.stride(0)
+    if ACT_BF16:
+        lo = None
     dev = prior.device
     if dev not in _TILE_COUNTER:
         _TILE_COUNTER[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -406,13 +414,37 @@ def live_weight_workspaces():
     return [e[0] for e in _W_CACHE.values()] + [t for e in _P_CACHE.values() for t in e[:2]]
 
 
+TC_MAX_N = 256         # output columns of one tcgen05 GEMM launch (one TMEM accumulator buffer)
+TC_MAX_N_SPLIT = 512   # wider outputs are tiled over N: one launch per <= 256-column slice of W
+
+
 def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=None, dots=None, relu=True,
-                     k_seg=0, k_seg_pitch=0):
+                     k_seg=0, k_seg_pitch=0, single_ok=False):
     """tcgen05 split-bf16 GEMM whose A operand already lives in bf16 hi/lo planes [M, >=K].
+    ``single_ok``: this call may run as ONE bf16 product when ``ACT_BF16`` is on (the node-update GEMMs; the small
+    relation-table GEMMs always keep the three-product fp32-class path).
     Writes any of: fp32 ``out`` [M,N]; ``out_planes`` (hi, lo) [M, >=N] (next layer's h columns);
-    ``dots`` [2*M] = the two column-half partial sums of out @ w_score."""
-    M = a_hi.shape[0]
+    ``dots`` [2*M] = the two column-half partial sums of out @ w_score.
+    N > 256 (cfg5: entity_dim 400) is tiled over the output columns: one launch per slice of W rows."""
     N = W.shape[0]
+    if N > TC_MAX_N:
+        nsl = (N + TC_MAX_N - 1) // TC_MAX_N
+        step = ((N + nsl - 1) // nsl + 15) // 16 * 16
+        part = None
+        for n0 in range(0, N, step):
+            n1 = min(N, n0 + step)
+            d = torch.empty_like(dots) if (dots is not None and n0 > 0) else dots
+            linear_tc_planes(a_hi, a_lo, K, W[n0:n1], None if bias is None else bias[n0:n1],
+                             out=None if out is None else out[:, n0:n1],
+                             out_planes=None if out_planes is None else (out_planes[0][:, n0:n1], out_planes[1][:, n0:n1]),
+                             w_score=None if w_score is None else w_score[n0:n1], dots=d, relu=relu, k_seg=k_seg,
+                             k_seg_pitch=k_seg_pitch, single_ok=single_ok)
+            if dots is not None and n0 > 0:
+                part = d if part is None else part + d
+        if part is not None:
+            dots += part
+        return out
+    M = a_hi.shape[0]
     assert a_hi.dtype == torch.bfloat16 and a_hi.stride(1) == 1 and a_hi.stride(0) == a_lo.stride(0)
     if k_seg and k_seg_pitch > k_seg:
         assert K % k_seg_pitch == 0 and W.shape[1] == K // k_seg_pitch * k_seg
@@ -423,7 +455,8 @@ def linear_tc_planes(a_hi, a_lo, K, W, bias, out=None, out_planes=None, w_score=
     nbytes = L.gr_linear_tc_planes_workspace_bytes(N, K)
     ws, presplit = _weight_ws(W, N, K, k_seg, k_seg_pitch, nbytes)
     chi, clo = out_planes if out_planes is not None else (None, None)
-    flags = (LINEAR_RELU if relu else 0) | (LINEAR_W_PRESPLIT if presplit else 0)
+    flags = (LINEAR_RELU if relu else 0) | (LINEAR_W_PRESPLIT if presplit else 0) | \
+        (LINEAR_BF16_SINGLE if (ACT_BF16 and single_ok) else 0)
     with _OpTimer("gemm_tc", (M, N, K)):
         rc = L.gr_linear_tc_planes(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(W), W.stride(0), _p(bias),
                                    _p(out), out.stride(0) if out is not None else 0,
@@ -459,7 +492,7 @@ class RelFeatures:
 
 
 def _tc_ok(n_out, k_in):
-    return bool(TC_LINEAR) and 8 <= n_out <= 256 and k_in >= 8
+    return bool(TC_LINEAR) and 8 <= n_out <= TC_MAX_N_SPLIT and k_in >= 8
 
 
 def rel_features_from_embeddings(embs, W, bias):

@@ -44,6 +44,8 @@ typedef enum gr_status {
 /* flags for gr_linear */
 #define GR_LINEAR_RELU 1u        /* C = relu(A W^T + b)                                      */
 #define GR_LINEAR_EXACT_FP32 2u  /* force the fp32 SIMT kernel (no split-bf16 tensor-core path) */
+#define GR_LINEAR_BF16_SINGLE 8u /* gr_linear_tc_planes: bf16 activation storage -- ONE product A_hi W_hi (A_lo ignored, may
+                                    be NULL); bf16-input / fp32-accumulate accuracy, a third of the tensor work   */
 #define GR_LINEAR_W_PRESPLIT 4u  /* gr_linear_tc_planes: the workspace still holds the bf16 hi/lo split of the same
                                   * W (same N, K, k_seg, k_seg_pitch) from an earlier call: skip the conversion pass.
                                   * For inference with fixed weights (weight pre-formatting, done once per weight

@@ -263,3 +263,50 @@ def test_sparse_prior_fastpath_matches_dense_path(kw):
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     _, _, want = O.forward(sd, args, S.WEBQSP_NUM_ENTITY, S.WEBQSP_NUM_WORD, b)
     assert ((outs[True][0].cpu() - want).abs() / want.clamp_min(1e-30)).max().item() < 1e-3
+
+
+def test_bf16_activation_storage_tracks_fp32():
+    """BASELINE configs[2] ("bf16"): activations stored as ONE bf16 plane (aggregation writes no lo plane, the e2e GEMM
+    runs one bf16 product), fp32 tables / accumulation / scores.  Stated tolerance: answer probabilities within 5 %
+    relative of the fp32 path on entries above 1e-6 (bf16 inputs, K = 1000, 6 layers), argmax and row sums intact."""
+    c = dict(S.CONFIGS["cfg2"], B=4, N=256, E=900, T=2)
+    m, args = _model(c)
+    b = S.make_batch(51, B=c["B"], N=c["N"], E=c["E"], with_weights=False, n_real="ragged")
+    _, pred32, d32, _ = m(b)
+    d32 = d32.clone()
+    ops.ACT_BF16 = True
+    try:
+        _, pred16, d16, _ = m(b)
+        d16 = d16.clone()
+        gs = G.GraphedStep(m, S.WEBQSP_NUM_ENTITY)
+        assert torch.equal(gs(b).pred_dist, d16)                  # graph replay == eager in this mode too
+    finally:
+        ops.ACT_BF16 = False
+    big = d32 > 1e-6
+    rel = ((d16 - d32).abs()[big] / d32[big]).max().item()
+    print("bf16 activation storage: max relative deviation from the fp32 path %.2e" % rel)
+    assert 0 < rel < 5e-2
+    assert torch.allclose(d16.sum(1), torch.ones_like(d16.sum(1)), atol=1e-4)
+    assert ((d16 == 0) == (d32 == 0)).all()                       # pads stay exactly zero
+
+
+def test_entity_dim_400_runs_on_the_tensor_core_path():
+    """cfg5's feature width (D = 400 > 256 TMEM accumulator columns): the GEMM is tiled over the output columns (two
+    launches per layer); same numbers as the exact-fp32 SIMT path within the split-bf16 bound."""
+    c = dict(S.CONFIGS["cfg5"], B=2, N=300, E=1200, T=2)
+    m, args = _model(c)
+    b = S.make_batch(52, B=2, N=300, E=1200, with_weights=False, powerlaw=True)
+    assert m.reasoning.__class__._alloc is not None
+    _, _, d_tc, _ = m(b)
+    assert m.reasoning.use_planes                                  # the plane / tcgen05 data flow was taken
+    d_tc = d_tc.clone()
+    ops.TC_LINEAR = False
+    try:
+        _, _, d_ref, _ = m(b)
+        assert not m.reasoning.use_planes
+    finally:
+        ops.TC_LINEAR = True
+    big = d_ref > 1e-12
+    rel = ((d_tc - d_ref).abs()[big] / d_ref[big]).max().item()
+    print("D=400 tcgen05 (N-tiled) vs fp32 SIMT: max relative deviation %.2e" % rel)
+    assert rel < 1e-3
