@@ -39,6 +39,8 @@ WORKLOADS = {
     "cfg3": "batch=256 CWQ-shape synthetic subgraphs (~10k nodes, ~40k edges, 4 hops)",
     "cfg4": "batch=1024 WebQSP-shape subgraphs sharded across 8xB200 = 128 questions per GPU (weak scaling)",
     "cfg5": "stress: 100k-node / 1M-edge synthetic subgraph, 400-dim feat, 3 hops",
+    "d50": "batch=64 WebQSP-shape subgraphs at the PUBLISHED model shape (gnn/README.md:19: entity_dim 50, num_iter 3, "
+           "num_ins 2, num_gnn 3)",
 }
 
 
@@ -48,7 +50,12 @@ def per_gpu_config(name):
     c = dict(S.CONFIGS[name])
     if name == "cfg4":
         c["B"] = c["B"] // 8
+    if _BATCH_OVERRIDE:
+        c["B"] = _BATCH_OVERRIDE
     return c
+
+
+_BATCH_OVERRIDE = None
 
 
 def parse():
@@ -58,6 +65,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=None, help="override the questions per GPU of the config")
     ap.add_argument("--cpu-sample", type=int, default=None,
                     help="questions per CPU step (default: 8 for the cpu_baseline leg, the whole batch -- at most 64 -- "
                          "for --impl reference)")
@@ -531,7 +539,9 @@ def run_ours(a):
 
 
 def main():
+    global _BATCH_OVERRIDE
     a = parse()
+    _BATCH_OVERRIDE = a.batch
     if a.impl == "reference":
         run_reference(a)
     else:

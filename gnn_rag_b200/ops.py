@@ -703,9 +703,10 @@ def rank_candidates(dist, local_entity, query_entities, pad_id, eps):
     return cand_idx, cand_count, cand_total
 
 
-def shortest_path_nodes(g, source_idx, source_cnt, target_idx, target_cnt):
+def shortest_path_nodes(g, source_idx, source_cnt, target_idx, target_cnt, return_distances=False):
     """source_idx int32[B,S], target_idx int32[B,T] local indices (+counts) ->
-    (on_path uint8[B,N], pair_dist int32[B,S,T])."""
+    (on_path uint8[B,N], pair_dist int32[B,S,T]); with ``return_distances`` also the BFS distance arrays the kernel
+    leaves in its workspace: int32 [B, S+T, N] (sources first), -1 = unreachable."""
     B, N = g.B, g.N
     S, T = source_idx.shape[1], target_idx.shape[1]
     dev = source_idx.device
@@ -719,4 +720,6 @@ def shortest_path_nodes(g, source_idx, source_cnt, target_idx, target_cnt):
                                   _p(target_idx.contiguous()), _p(target_cnt.contiguous()), T,
                                   _p(on_path), _p(pair_dist), B, N, _p(ws), nbytes, _stream())
     _lib.check(rc)
+    if return_distances:
+        return on_path, pair_dist, ws[: B * (S + T) * N * 4].view(torch.int32).view(B, S + T, N)
     return on_path, pair_dist

@@ -169,6 +169,8 @@ CONFIGS = {
     "cfg3": dict(B=256, N=10_000, E=40_000, D=200, T=2, K=4, I=3),
     "cfg4": dict(B=1024, N=2000, E=6000, D=200, T=3, K=3, I=2),
     "cfg5": dict(B=1, N=100_000, E=1_000_000, D=400, T=3, K=3, I=2),
+    # the shape of the published checkpoints (gnn/README.md:19, gnn/scripts/rearev_cwq.sh:14): entity_dim 50
+    "d50": dict(B=64, N=2000, E=6000, D=50, T=3, K=3, I=2),
 }
 
 
