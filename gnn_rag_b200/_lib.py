@@ -31,6 +31,8 @@ SIGNATURES = {
                              c_u32, c_void_p, c_size, c_void_p]),
     "gr_aggregate": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64,
                              c_i64, c_i64, c_f32p, c_int, c_int, c_int, c_int, c_i64, c_void_p]),
+    "gr_aggregate_backward": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_i64,
+                                      c_i64, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_i64, c_void_p]),
     "gr_aggregate_dual": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p,
                                   c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_i64, c_i64,
                                   c_void_p, c_void_p, c_i64,

@@ -71,6 +71,57 @@ def _aggregate(table, ins_j, prior_flat, facts, src, dst, Nt):
     return _scatter_rows(fact_val * prior.unsqueeze(1), dst, Nt)
 
 
+USE_KERNELS = True      # CUDA tensors: aggregation forward / backward through the hand-written kernels (below)
+
+
+class _AggregateFn(torch.autograd.Function):
+    """out[n, j, :] = sum_{e -> n} w_e^2 p[src_e] relu(table[rel_e] * ins[b, j]) for all instructions j of one direction:
+    forward = gr_aggregate (csrc/aggregate.cu), backward = gr_aggregate_backward (csrc/aggregate_bwd.cu)."""
+
+    @staticmethod
+    def forward(ctx, table, ins, prior, graph, direction, w):
+        from . import ops
+        out = ops.aggregate(graph, direction, prior.detach(), table.detach(), ins.detach(), w=w)
+        ctx.save_for_backward(table, ins, prior)
+        ctx.graph, ctx.direction, ctx.w = graph, direction, w
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import ops
+        table, ins, prior = ctx.saved_tensors
+        gt, gi, gp = torch.zeros_like(table), torch.zeros_like(ins), torch.zeros_like(prior)
+        ops.aggregate_backward(ctx.graph, ctx.direction, prior, table.contiguous(), ins.contiguous(),
+                               grad_out.contiguous(), gt, gi, gp, ctx.w)
+        return gt, gi, gp, None, None, None
+
+
+def _kernel_graph(model, batch, device, D, I):
+    """CSR of the batch for the kernel path, or None (CPU tensors / shapes the backward kernel does not cover)."""
+    if not (USE_KERNELS and device.type == "cuda" and D <= 256 and I <= 4):
+        return None
+    from . import batching
+    return batching.stage_batch(batch, device, model.num_relation + 1, model.normalized_gnn, False).graph
+
+
+def _neighbours(table_f, table_i, ins, dist, facts, graph, Nt):
+    """[Nt, I, n_dir, D] neighbour messages of one layer (reasongnn.py:150-156), kernel or torch path."""
+    I = ins.shape[1]
+    if graph is not None:
+        outs = [_AggregateFn.apply(table_f.contiguous(), ins, dist, graph, "fwd", graph.w_t).view(Nt, I, 1, -1)]
+        if table_i is not None:
+            outs.append(_AggregateFn.apply(table_i.contiguous(), ins, dist, graph, "inv", graph.w_h).view(Nt, I, 1, -1))
+        return torch.cat(outs, dim=2)
+    pf = dist.reshape(-1)
+    reps = []
+    for j in range(I):
+        r = [_aggregate(table_f, ins[:, j], pf, facts, facts.heads, facts.tails, Nt)]
+        if table_i is not None:
+            r.append(_aggregate(table_i, ins[:, j], pf, facts, facts.tails, facts.heads, Nt))
+        reps.append(torch.stack(r, dim=1))
+    return torch.stack(reps, dim=1)
+
+
 def _instructions(enc, q_input):
     """base_encoder.py:73-114 on top of encode_question; returns [B, num_ins, D]."""
     enc.encode_question_train(q_input)
@@ -188,16 +239,14 @@ def rearev_forward(model, batch):
         tables.append((tf, ti))
     dist_history = [seed_dist]
     dist = seed_dist
+    graph = _kernel_graph(model, batch, h.device, D, I)
     for _t in range(model.num_iter):
         dist = seed_dist
+        ins = torch.stack(ins_list, dim=1)                                  # [B, I, D]
         for k in range(model.num_gnn):
             tf, ti = tables[k]
-            pf = dist.reshape(-1)
-            reps = [h]
-            for j in range(I):
-                reps.append(_aggregate(tf, ins_list[j], pf, facts, facts.heads, facts.tails, Nt))
-                reps.append(_aggregate(ti, ins_list[j], pf, facts, facts.tails, facts.heads, Nt))
-            h = F.relu(getattr(layer, "e2e_linear" + str(k))(drop(torch.cat(reps, dim=1))))
+            nb = _neighbours(tf, ti, ins, dist, facts, graph, Nt)           # [Nt, I, 2, D]: (j, direction) as in :150-156
+            h = F.relu(getattr(layer, "e2e_linear" + str(k))(drop(torch.cat([h, nb.reshape(Nt, -1)], dim=1))))
             score = layer.score_func(drop(h)).view(B, N) + (1 - mask) * VERY_NEG_NUMBER
             dist = F.softmax(score, dim=1)
         dist_history.append(dist)
@@ -232,10 +281,11 @@ def nsm_forward(model, batch):
     drop = layer.linear_drop_train
     dist = seed_dist
     dist_history = [dist]
+    graph = _kernel_graph(model, batch, h.device, D, 1)
     for k in range(model.num_step):
         table = getattr(layer, "rel_linear" + str(k))(rel_f)
         pf = dist.reshape(-1)
-        nb = _aggregate(table, instructions[:, k], pf, facts, facts.heads, facts.tails, Nt)
+        nb = _neighbours(table, None, instructions[:, k:k + 1], dist, facts, graph, Nt).reshape(Nt, D)
         h = F.relu(getattr(layer, "e2e_linear" + str(k))(drop(torch.cat([h, nb], dim=1))))
         m = mask
         if layer.reason_kb:                                                # nsm_gnn.py:98-101

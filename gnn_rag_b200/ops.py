@@ -255,6 +255,24 @@ def aggregate(g, direction, prior, table, ins, out=None, out_col0=0, seg_stride=
     return out
 
 
+def aggregate_backward(g, direction, prior, table, ins, grad_out, grad_table, grad_ins, grad_prior, w=None):
+    """Accumulate the gradients of :func:`aggregate` (same ``direction`` / CSR) into grad_table [R1,D], grad_ins
+    [B,I,D], grad_prior [B,N]; grad_out [B*N, I*D] contiguous rows (csrc/aggregate_bwd.cu)."""
+    prior = _cuda(prior, torch.float32, "prior").contiguous()
+    table = _cuda(table, torch.float32, "table").contiguous()
+    ins = _cuda(ins, torch.float32, "ins").contiguous()
+    grad_out = _cuda(grad_out, torch.float32, "grad_out")
+    B, I, D = ins.shape
+    assert grad_out.stride(1) == 1 and grad_table.is_contiguous() and grad_ins.is_contiguous() and grad_prior.is_contiguous()
+    rp, src, rel = (g.rowptr_t, g.src_t, g.rel_t) if direction == "fwd" else (g.rowptr_h, g.src_h, g.rel_h)
+    with _OpTimer("aggregation_bwd"):
+        rc = _L().gr_aggregate_backward(_p(rp), _p(src), _p(rel), _p(w), _p(prior), _p(table), _p(ins), _p(grad_out),
+                                        grad_out.stride(0), 0, D, _p(grad_table), _p(grad_ins), _p(grad_prior),
+                                        B, g.N, D, I, g.F, _stream())
+    _lib.check(rc)
+    STATS.launches += 1
+
+
 def aggregate_dual(g, prior, table_fwd, table_inv, ins, out, out_col0, w_t=None, w_h=None, planes=None,
                    seg_pitch=0):
     """Both directions of one ReaRev layer: out[:, out_col0 + (2j+dir)*D : +D] (reasongnn.py:150-161).

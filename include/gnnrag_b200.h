@@ -163,6 +163,18 @@ int gr_aggregate(const int32_t* rowptr, const int32_t* src, const int32_t* rel, 
                  float* out, int64_t out_row_stride, int64_t out_col0, int64_t seg_stride,
                  float* possible, int B, int N, int D, int I, int64_t F, void* stream);
 
+/* Backward of gr_aggregate (csrc/aggregate_bwd.cu; the kernel behind model(batch, training=True), gnn/train_model.py:222):
+ * given grad_out[n, grad_col0 + j*seg_stride + d] = dL/dout it ACCUMULATES (+=, caller zeroes)
+ *     grad_table[r, :] += sum_{e: rel_e = r} c_e sum_j grad_out[n_e, j, :] * ins[b, j, :] * [table[r] * ins[b, j] > 0]
+ *     grad_ins[b, j, :] += sum_{e in b} c_e grad_out[n_e, j, :] * table[rel_e, :] * [table[rel_e] * ins[b, j] > 0]
+ *     grad_prior[s]     += sum_{e: src_e = s} w_e^2 sum_j <grad_out[n_e, j, :], relu(table[rel_e] * ins[b, j])>
+ * over the same destination CSR as the forward call.  D <= 256, I <= 4.  fp32 atomics: summation order is not
+ * deterministic (neither is the reference's sparse.mm backward on CUDA). */
+int gr_aggregate_backward(const int32_t* rowptr, const int32_t* src, const int32_t* rel, const float* w,
+                          const float* prior, const float* table, const float* ins, const float* grad_out,
+                          int64_t grad_row_stride, int64_t grad_col0, int64_t seg_stride, float* grad_table,
+                          float* grad_ins, float* grad_prior, int B, int N, int D, int I, int64_t F, void* stream);
+
 int gr_aggregate_dual(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t,
                       const float* w_t, const int32_t* rowptr_h, const int32_t* src_h,
                       const int32_t* rel_h, const float* w_h, const float* prior,
