@@ -65,6 +65,12 @@ def test_training_on_gpu_through_the_aggregation_kernels(name):
     assert autograd_path.USE_KERNELS
     m, batch, t = _load(name, device="cuda")
     m = m.cuda()
+    m.train()                                           # cuDNN's LSTM backward needs training mode ...
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.eval()                                  # ... the dropouts stay the identity, as in the generator
+    if hasattr(m.instruction, "node_encoder") and not isinstance(m.instruction.node_encoder, torch.nn.LSTM):
+        m.instruction.node_encoder.eval()               # HuggingFace encoder: its internal dropouts off
     if getattr(m, "rel_texts", None) is not None:
         g = Golden(name)
         m.encode_rel_texts(g.rel_texts, g.rel_texts_inv)
