@@ -72,6 +72,15 @@ def _aggregate(table, ins_j, prior_flat, facts, src, dst, Nt):
 
 
 USE_KERNELS = True      # CUDA tensors: aggregation forward / backward through the hand-written kernels (below)
+HOST_CHECK = False      # tests only: let a CPU-resident model evaluate this restatement with torch CPU ops, so that the
+                        # ``-m "not gpu"`` suite can hold it against the reference's gradients.  Off (the product):
+                        # ``model(batch, training=True)`` on a CPU model raises, like the inference path.
+
+
+def _require_cuda(dev):
+    if dev.type != "cuda" and not HOST_CHECK:
+        raise RuntimeError("gnn_rag_b200 runs on CUDA only: move the model to a B200 (model.cuda()); there is no CPU "
+                           "path (training=True included)")
 
 
 class _AggregateFn(torch.autograd.Function):
@@ -204,6 +213,7 @@ def eval_metric(model, pred_dist, answer_dist, seed_dist, local_entity):
 def _stage(model, batch):
     local_entity, query_entities, kb_adj_mat, q_input, seed_dist, _tb, answer_dist = batch[:7]
     dev = model.word_embedding.weight.device
+    _require_cuda(dev)
 
     def t(x, dtype):
         x = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))

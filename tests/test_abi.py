@@ -90,6 +90,5 @@ def test_models_refuse_cpu():
     m = G.ReaRev(args, 100, 10, 20)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(S.make_batch(0, 2, 10, 20, 100, 10, 20))
-    # training=True is the differentiable torch path (autograd_path.py): plain torch, any device
-    loss, pred, dist, tp = m(S.make_batch(0, 2, 10, 20, 100, 10, 20), training=True)
-    assert loss.requires_grad and len(tp) == 2
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(S.make_batch(0, 2, 10, 20, 100, 10, 20), training=True)

@@ -1,7 +1,8 @@
 """``model(batch, training=True)`` -- the call of Trainer_KBQA.train_epoch (gnn/train_model.py:222) -- against loss,
 train-time metrics and parameter gradients recorded from the UNMODIFIED reference (tests/golden/train/*.npz, made by
-tests/golden/make_train_golden.py).  The differentiable path is plain torch, so it is checked on CPU tensors here
-(the product's inference path stays CUDA-only) and on the GPU in test_configs_gpu.py."""
+tests/golden/make_train_golden.py).  The differentiable path is torch autograd around the aggregation kernels; the CPU
+tests here switch ``autograd_path.HOST_CHECK`` on to evaluate its torch restatement on CPU tensors (the product refuses
+a CPU model), the ``gpu`` tests below run it through the kernels."""
 import os
 
 import numpy as np
@@ -10,6 +11,24 @@ import torch
 
 import gnn_rag_b200 as G
 from golden_io import GOLDEN_DIR, Golden
+
+from gnn_rag_b200 import autograd_path
+
+
+@pytest.fixture(autouse=True)
+def _host_check():
+    old = autograd_path.HOST_CHECK
+    autograd_path.HOST_CHECK = True
+    yield
+    autograd_path.HOST_CHECK = old
+
+
+def test_training_refuses_a_cpu_model_outside_the_host_check():
+    autograd_path.HOST_CHECK = False
+    m, batch, _ = _load("rearev_small")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(batch, training=True)
+
 
 CASES = ["rearev_small", "rearev_norm", "rearev_posemb", "rearev_sharp_ties", "nsm_small", "nsm_reason_kb",
          "rearev_sbert_reltext"]
