@@ -102,7 +102,8 @@ def test_training_on_gpu_through_the_aggregation_kernels(name):
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         loss.backward()
     # tolerance: 5e-3 of the tensor's own scale (GPU summation orders, fp32 atomics, cuDNN's LSTM) plus 1e-5 of the
-    # largest gradient in the model (tensors whose true gradient is ~0, e.g. the score bias, hold only rounding noise)
+    # largest gradient in the model (tensors whose true gradient is ~0, e.g. the score bias, hold only rounding noise;
+    # 1e-7 absolute for the same reason when the whole model's gradients are small)
     gmax = max(float(np.abs(t[k]).max()) for k in t.files if k.startswith("grad/"))
     checked = 0
     for k, p in m.named_parameters():
@@ -112,7 +113,7 @@ def test_training_on_gpu_through_the_aggregation_kernels(name):
         want = t[key]
         got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(want)
         scale = np.abs(want).max()
-        assert np.abs(got - want).max() <= 5e-3 * scale + 1e-5 * gmax, (k, np.abs(got - want).max(), scale, gmax)
+        assert np.abs(got - want).max() <= 5e-3 * scale + 1e-5 * gmax + 1e-7, (k, np.abs(got - want).max(), scale, gmax)
         checked += 1
     assert checked >= 20
 
