@@ -4,7 +4,7 @@ The batched graph is block diagonal by construction (gnn/dataset_load.py:483,492
 node rows ``[b*N,(b+1)*N)`` and its facts never leave the block; softmax and instructions are per question.
 So rank ``g`` of ``G`` takes a contiguous question range, weights are replicated, there is NO communication
 during the forward, and one all-gather of the ``[B/G, N]`` answer scores at the end.  The partition is
-pure index arithmetic and is tested on CPU with gloo (tests/test_parallel.py).
+pure index arithmetic and is tested on CPU with gloo, world_size 2 (tests/test_host_logic.py).
 """
 import numpy as np
 import torch
