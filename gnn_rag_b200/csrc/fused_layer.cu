@@ -1,0 +1,753 @@
+// One ReaRev GNN layer with a dense prior as ONE kernel: relation-typed aggregation of both directions and all
+// instructions  ->  e2e linear (+ bias, relu, score dot)  (ReasonGNNLayer.forward, gnn/modules/kg_reasoning/
+// reasongnn.py:134-174: reason_layer / reason_layer_inv :61-116, the torch.cat + e2e_linear of :158-163, the
+// score_func dot of :165).
+//
+// The unfused pair (aggregate_abs.cu -> linear_tc.cu) writes the 2*I neighbour segments of the layer-input matrix to
+// HBM (0.41 GB per layer at cfg2) and reads them straight back as the GEMM's A operand.  Here the neighbour k-blocks
+// never leave the SM: aggregation warps produce them directly into the UMMA shared-memory operand slots (K-major,
+// SWIZZLE_64B, bf16 hi/lo planes -- the layout TMA would have written), only the h segment and W come from memory.
+//
+// Per 128-row tile the K dimension is walked in G column groups of 32; group g holds, in this order,
+//     Y(dir 0, j = 0..I-1), Y(dir 1, j = 0..I-1), H              (T = 2*I + 1 k-blocks of 32 columns)
+// i.e. column block g of every segment of [h | nb_0^fwd | nb_0^inv | nb_1^fwd | ...].  The S = sum c*v / Q = sum c*|v|
+// accumulation of aggregate_abs.cu is instruction independent, so one pass over a row's in-edges restricted to the 32
+// columns of group g yields the I blocks Y(dir, 0..I-1) together.  W is pre-formatted once per weight version in this
+// K order (fused_w_split_kernel).  Arithmetic per element is the one of aggregate_abs.cu (same edge order, same FMA
+// sequence, same hi/lo split), so the A operand is bit-identical to the unfused path; only the order in which the
+// tensor core accumulates k-blocks differs (fp32 rounding, ~1e-7).
+//
+// Warp roles (768 threads, one CTA per SM, clusters of 2 share W by TMA multicast):
+//   warp 0      TMA producer: W k-blocks into a 3-stage ring, the H block of every group into its A slot
+//   warp 1      MMA issuer (one thread): tcgen05.mma cta_group::1 kind::f16, 3 products per k-step
+//   warp 2      TMEM allocator (2 x 256 columns: epilogue of tile i overlaps the mainloop of tile i+1)
+//   warp 3      edge stager: row pointers, {table byte offset, c_f} per in-edge of both CSRs, the instructions of the
+//               tile's <= 2 questions -> double-buffered shared-memory tile descriptor
+//   warps 4-7   epilogue: tcgen05.ld -> bias + relu + score dot -> fp32 h / bf16 planes via TMA stores
+//   warps 8-23  aggregation: warp a owns tile rows 8a .. 8a+7; a half-warp owns a row at a time, lane = 2 columns of
+//               the 32-column group (one 128-byte line of the padded relation table per gathered edge); 4 row pairs x 4
+//               edges = 16 independent 8-byte loads in flight per lane
+// A slots are dedicated: slot t < 2I is always written by the aggregation warps, slot 2I always by TMA, so every slot
+// barrier flips once per group and the parity is the group counter.
+#include <algorithm>
+#include <cstddef>
+
+#include "tcgen05.cuh"
+
+namespace gr {
+namespace {
+
+using namespace tc;
+
+constexpr int BK = 32;                       // k-block width: 64-byte rows, SWIZZLE_64B
+constexpr int kAggWarps = 16;
+constexpr int kEpiWarps = 4;
+constexpr int kFirstEpi = 4, kFirstAgg = 8;
+constexpr int kThreads = (kFirstAgg + kAggWarps) * 32;      // 768
+constexpr int kNW = 3;                       // W ring stages
+constexpr int kECap = 1024;                  // staged in-edges per direction per tile (mean 512 at cfg2); rest: slow path
+constexpr int kXCols = 256;                  // instruction columns kept per question (zero padded)
+constexpr int kPnRowBytes = 1024;            // padded relation table: 256 fp32 per row (gr_pad_table256)
+constexpr int kABytes = BM * BK * 2;         // one bf16 plane of an A slot: 8 KB
+constexpr int kOutBytes = BM * 16 * 4 + 2 * BM * 16 * 2;    // epilogue staging: fp32 8 KB + hi 4 KB + lo 4 KB
+constexpr int kAccStride = 256;
+
+struct FDir {
+  const int32_t* rowptr;
+  const int32_t* src;
+  const int32_t* rel;
+  const float* w;          // optional per-edge weights (normalized_gnn)
+  const char* pn;          // zero-padded relation table [R1, 256] fp32
+};
+
+struct FParams {
+  FDir dir[2];
+  const float* prior;      // [Nt]
+  const float* ins;        // [B, I, D]
+  const float* bias;
+  float* C;                // optional fp32 output [Nt, N]
+  int64_t ldc;
+  const float* w_score;
+  float* dots;             // [2 * Nt]: dots[m] = score dot, dots[Nt + m] = 0 (layout of gr_linear_tc_planes)
+  int M, N, n_pad, D, B, Nq, G, ksteps_last, num_tiles;
+  int has_planes;
+  uint32_t flags;
+};
+
+template <int NI>
+struct alignas(16) ETile {
+  int2 rc[2][kECap];                  // {table byte offset rel * 1024, float_as_int(c_f)}
+  float x[2][NI][kXCols];             // raw instruction vectors of the tile's two questions
+  int32_t rowptr[2][BM + 4];          // global edge indices
+  int32_t nrows, lr_switch, pad_[2];
+};
+
+template <int NI>
+constexpr size_t fused_smem_bytes(int n_pad) {
+  return 1024 /*align slack*/ + (size_t)(2 * NI + 1) * 2 * kABytes + (size_t)kNW * 2 * n_pad * BK * 2 + kOutBytes +
+         2 * sizeof(ETile<NI>) + 64 * 8 + 16 + 2 * 256 * 4;
+}
+
+// W [N, (2I+1)*D] fp32 -> hi/lo planes [N, G*T*32] in the kernel's K order (see the header comment)
+__global__ void fused_w_split_kernel(const float* __restrict__ W, int64_t ldw, int N, int D, int I, int G,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int T = 2 * I + 1;
+  const int64_t Kp = (int64_t)G * T * BK;
+  const int64_t total = (int64_t)N * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / Kp;
+    const int k = (int)(i - n * Kp);
+    const int blk = k / BK, c = k % BK;
+    const int g = blk / T, t = blk % T;
+    // t < 2I: Y(dir = t / I, j = t % I) -> segment 1 + 2j + dir;  t == 2I: the h segment
+    const int seg = t == 2 * I ? 0 : 1 + 2 * (t % I) + t / I;
+    const int col = g * BK + c;
+    const float v = col < D ? __ldg(W + n * ldw + (int64_t)seg * D + col) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ float2 ldg2(const char* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+// explicit shared-state-space accesses (the carve-up of the dynamic buffer goes through integer alignment, after
+// which the compiler would fall back to generic loads / stores)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// edge stager (one warp): tile descriptor of tile `tile` into `et`
+// ---------------------------------------------------------------------------------------------------------
+template <int NI>
+__device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int tile, int lane) {
+  const int64_t r0 = (int64_t)tile * BM;
+  const int nrows = tile < p.num_tiles ? (int)min((int64_t)BM, (int64_t)p.M - r0) : 0;
+  if (lane == 0) {
+    et.nrows = nrows;
+    const int b0 = nrows > 0 ? (int)(r0 / p.Nq) : 0;
+    et.lr_switch = p.Nq - (int)(r0 - (int64_t)b0 * p.Nq);       // first tile row of question b0 + 1 (Nq >= BM)
+  }
+  if (nrows == 0) return;
+  const int b0 = (int)(r0 / p.Nq);
+  int eb[2], ne[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int32_t* rp = p.dir[d].rowptr + r0;
+    const int e0 = __ldg(rp), e1 = __ldg(rp + nrows);
+#pragma unroll
+    for (int k = 0; k < (BM + 32) / 32; ++k) {
+      const int i = lane + 32 * k;
+      if (i <= nrows) et.rowptr[d][i] = __ldg(rp + i);
+    }
+    eb[d] = e0;
+    ne[d] = min(e1 - e0, kECap);
+  }
+  for (int i = lane; i < 2 * NI * kXCols; i += 32) {
+    const int c = i % kXCols, j = (i / kXCols) % NI, q = i / (kXCols * NI);
+    const int b = b0 + q;
+    (&et.x[0][0][0])[i] = (c < p.D && b < p.B) ? __ldg(p.ins + ((int64_t)b * NI + j) * p.D + c) : 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const FDir& dd = p.dir[d];
+    for (int i0 = 0; i0 < ne[d]; i0 += 128) {
+      int sidx[4], ridx[4];
+      float wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + 32 * u;
+        const bool ok = i < ne[d];
+        sidx[u] = ok ? __ldg(dd.src + eb[d] + i) : 0;
+        ridx[u] = ok ? __ldg(dd.rel + eb[d] + i) : 0;
+        wv[u] = (ok && dd.w) ? __ldg(dd.w + eb[d] + i) : 1.0f;
+      }
+      float pr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pr[u] = __ldg(p.prior + sidx[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + 32 * u;
+        if (i < ne[d])
+          et.rc[d][i] = make_int2((int)((uint32_t)ridx[u] * (uint32_t)kPnRowBytes),
+                                  __float_as_int(wv[u] * (wv[u] * pr[u])));             // reasongnn.py:80-84
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// aggregation: one pass = (direction d, column group g) for this warp's 8 rows -> I A-operand blocks
+// ---------------------------------------------------------------------------------------------------------
+// y = xp * (Q + S) + xn * (Q - S)  (xp = relu(x)/2, xn = relu(-x)/2), split into bf16 hi / lo, stored at the (row, column
+// pair) slot of the K-major SWIZZLE_64B operand tile: 16-byte chunk index XOR ((row >> 1) & 3)
+__device__ __forceinline__ void emit_pair(uint32_t slot, float2 xp, float2 xn, float2 U, float2 V) {
+  float2 y = __fmul2_rn(xp, U);
+  y = __ffma2_rn(xn, V, y);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(y.x, y.y);
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  const float2 r = __ffma2_rn(f, make_float2(-1.f, -1.f), y);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r.x, r.y);
+  sts_u32(slot, u);
+  sts_u32(slot + kABytes, *reinterpret_cast<const uint32_t*>(&l));
+}
+
+// one gather slot: if (k < rem) { {off, c} = staged edge; v = table[off + lane columns] }.  One asm block per slot keeps
+// the per-slot cost at four instructions (ISETP, LDS, IMAD.WIDE, LDG.64) and lets the 16 slots of a round issue
+// back to back; the outputs keep their old value when the slot is off (the matching FMAs are predicated the same way)
+__device__ __forceinline__ void gather_slot(float2& v, uint32_t edge_s, int rem, int k, const char* tb) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .u32 o;\n\t.reg .u64 a;\n\t"
+      "setp.gt.s32 q, %2, %3;\n\t"
+      "ld.shared.b32 o, [%4];\n\t"          // unconditional: the address always lies inside the tile descriptor
+      "mad.wide.u32 a, o, 1, %5;\n\t"
+      "@q ld.global.nc.v2.f32 {%0, %1}, [a];\n\t}"
+      : "+f"(v.x), "+f"(v.y)
+      : "r"(rem), "r"(k), "r"(edge_s), "l"(tb));
+}
+
+template <int NI>
+struct LaneX {                      // relu(+-x)/2 of one question at this lane's two columns of the group
+  float2 xp[NI], xn[NI];
+  __device__ __forceinline__ void load(uint32_t xs) {          // xs = smem address of x[q][0][col]
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const float2 x = lds_f2(xs + (uint32_t)(j * kXCols * 4));
+      xp[j] = make_float2(0.5f * fmaxf(x.x, 0.f), 0.5f * fmaxf(x.y, 0.f));
+      xn[j] = make_float2(0.5f * fmaxf(-x.x, 0.f), 0.5f * fmaxf(-x.y, 0.f));
+    }
+  }
+};
+
+template <int NI>
+__device__ __forceinline__ void agg_pass(const ETile<NI>& et, const FParams& p, int d, int g, int wa, int lane,
+                                         uint32_t a_slots) {
+  const int hw = lane >> 4, l16 = lane & 15;
+  const uint32_t et_s = smem_u32(&et);
+  const uint32_t rp_s = et_s + (uint32_t)offsetof(ETile<NI>, rowptr) + (uint32_t)d * (BM + 4) * 4u;
+  const int nrows = (int)lds_u32(et_s + (uint32_t)offsetof(ETile<NI>, nrows));
+  const int lr_switch = (int)lds_u32(et_s + (uint32_t)offsetof(ETile<NI>, lr_switch));
+  const FDir& dd = p.dir[d];
+  const char* tb = dd.pn + (g * BK + 2 * l16) * 4;
+  const int ebase = (int)lds_u32(rp_s);
+  const bool fits = (int)lds_u32(rp_s + (uint32_t)nrows * 4u) - ebase <= kECap;     // warp uniform
+  const uint32_t rc_base = et_s + (uint32_t)d * kECap * 8u;
+  uint32_t ptr[4];
+  int rem[4];
+  int maxn = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int lr = wa * 8 + 2 * i + hw;
+    int beg = 0;
+    rem[i] = 0;
+    if (lr < nrows) {
+      beg = (int)lds_u32(rp_s + (uint32_t)lr * 4u) - ebase;
+      rem[i] = (int)lds_u32(rp_s + (uint32_t)lr * 4u + 4u) - ebase - beg;
+    }
+    ptr[i] = rc_base + (uint32_t)beg * 8u;
+    maxn = max(maxn, rem[i]);
+  }
+  maxn = __reduce_max_sync(0xffffffffu, maxn);
+  float2 S[4], Q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) S[i] = Q[i] = make_float2(0.f, 0.f);
+  if (fits) {
+    float2 v[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[i][k] = make_float2(0.f, 0.f);
+    for (; maxn > 0; maxn -= 4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gather_slot(v[i][k], ptr[i] + 8u * k, rem[i], k, tb);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < rem[i]) {
+            const float c = lds_f32(ptr[i] + 8u * k + 4u);
+            const float2 cc = make_float2(c, c);
+            S[i] = __ffma2_rn(cc, v[i][k], S[i]);
+            Q[i] = __ffma2_rn(cc, make_float2(fabsf(v[i][k].x), fabsf(v[i][k].y)), Q[i]);
+          }
+        ptr[i] += 32u;
+        rem[i] -= 4;
+      }
+    }
+  } else {
+    // slow path (a tile whose in-edge slice overflows the staging buffer): one edge at a time, overflow from global
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int beg = (int)((ptr[i] - rc_base) >> 3);
+      for (int e = 0; e < rem[i]; ++e) {
+        const int idx = beg + e;
+        uint32_t off;
+        float c;
+        if (idx < kECap) {
+          off = lds_u32(rc_base + (uint32_t)idx * 8u);
+          c = lds_f32(rc_base + (uint32_t)idx * 8u + 4u);
+        } else {
+          const int64_t ge = (int64_t)ebase + idx;
+          const float w = dd.w ? dd.w[ge] : 1.0f;
+          c = w * (w * p.prior[dd.src[ge]]);
+          off = (uint32_t)dd.rel[ge] * (uint32_t)kPnRowBytes;
+        }
+        const float2 vv = ldg2(tb + off);
+        const float2 cc = make_float2(c, c);
+        S[i] = __ffma2_rn(cc, vv, S[i]);
+        Q[i] = __ffma2_rn(cc, make_float2(fabsf(vv.x), fabsf(vv.y)), Q[i]);
+      }
+    }
+  }
+  const float2 one = make_float2(1.f, 1.f), mone = make_float2(-1.f, -1.f);
+  const uint32_t xs = et_s + (uint32_t)offsetof(ETile<NI>, x) + (uint32_t)((g * BK + 2 * l16) * 4);
+  LaneX<NI> x;
+  int cur_q = -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int lr = wa * 8 + 2 * i + hw;
+    if (lr >= nrows) continue;
+    const int q = lr >= lr_switch ? 1 : 0;
+    if (q != cur_q) {
+      cur_q = q;
+      x.load(xs + (uint32_t)(q * NI * kXCols * 4));
+    }
+    const float2 U = __ffma2_rn(S[i], one, Q[i]), V = __ffma2_rn(S[i], mone, Q[i]);
+    const uint32_t off = (uint32_t)lr * 64u + ((uint32_t)((l16 >> 2) ^ ((lr >> 1) & 3)) << 4) + (uint32_t)(l16 & 3) * 4u;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) emit_pair(a_slots + (uint32_t)((d * NI + j) * 2 * kABytes) + off, x.xp[j], x.xn[j], U, V);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int NI, int CS>
+__global__ void __launch_bounds__(kThreads, 1)
+fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_constant__ CUtensorMap map_h_lo,
+                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                   const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c_hi,
+                   const __grid_constant__ CUtensorMap map_c_lo, const FParams p) {
+  constexpr int T = 2 * NI + 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_bytes = p.n_pad * BK * 2;
+  uint8_t* a_slots = smem;                                        // [T] x {hi 8 KB, lo 8 KB}
+  uint8_t* w_ring = a_slots + (size_t)T * 2 * kABytes;            // [kNW] x {W_hi, W_lo}
+  uint8_t* s_out = w_ring + (size_t)kNW * 2 * w_bytes;            // epilogue staging
+  ETile<NI>* etile = reinterpret_cast<ETile<NI>*>(s_out + kOutBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(etile) + 2 * sizeof(ETile<NI>));
+  uint64_t* wfull = bars;                 // [kNW]
+  uint64_t* wempty = wfull + kNW;         // [kNW]
+  uint64_t* afull = wempty + kNW;         // [T]
+  uint64_t* aempty = afull + T;           // [T]
+  uint64_t* tmem_full = aempty + T;       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint64_t* efull = tmem_empty + 2;       // [2]
+  uint64_t* eempty = efull + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 64);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);        // [256]
+  float* s_ws = s_bias + 256;                                     // [256]
+  for (int i = threadIdx.x; i < 256; i += kThreads) {
+    s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+    s_ws[i] = (p.w_score && i < p.N) ? p.w_score[i] : 0.f;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int ncluster = gridDim.x / CS, cid = blockIdx.x / CS;
+  const int ngroups = (p.num_tiles + CS - 1) / CS;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
+  const int G = p.G;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kNW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], CS); }
+    for (int t = 0; t < T; ++t) { mbar_init(&afull[t], t == T - 1 ? 1 : kAggWarps); mbar_init(&aempty[t], 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&efull[a], 32); mbar_init(&eempty[a], kAggWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2u * kAccStride)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CS > 1) cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // register file: 768 threads x 80 at launch; the control warpgroup (warps 0-3) and the epilogue warpgroup (4-7) hand
+  // registers back so that the four aggregation warpgroups can hold 16 gathers in flight per lane
+  // (the instruction sits at the top of each role's branch: ptxas budgets the code it dominates)
+  if (warp < kFirstEpi) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t wphase = 0, grp = 0;
+      int ws = 0;
+      const int w_rows = p.n_pad / CS;
+      const int w_slice = w_rows * BK * 2;
+      for (int tg = cid; tg < ngroups; tg += ncluster) {
+        const int m0 = (tg * CS + crank) * BM;
+        for (int g = 0; g < G; ++g, ++grp) {
+          for (int t = 0; t < T; ++t) {
+            const int kcol = (g * T + t) * BK;
+            mbar_wait(&wempty[ws], wphase ^ 1);
+            uint8_t* st = w_ring + (size_t)ws * 2 * w_bytes;
+            mbar_expect_tx(&wfull[ws], (uint32_t)(2 * w_bytes));
+            if (CS == 1) {
+              tma_load_2d(st, &map_w_hi, &wfull[ws], kcol, 0);
+              tma_load_2d(st + w_bytes, &map_w_lo, &wfull[ws], kcol, 0);
+            } else {
+              tma_load_2d_mc(st + crank * w_slice, &map_w_hi, &wfull[ws], kcol, crank * w_rows, kMask);
+              tma_load_2d_mc(st + w_bytes + crank * w_slice, &map_w_lo, &wfull[ws], kcol, crank * w_rows, kMask);
+            }
+            if (++ws == kNW) { ws = 0; wphase ^= 1; }
+            if (t == T - 1) {                                      // the h block of this group
+              mbar_wait(&aempty[t], (grp & 1) ^ 1);
+              uint8_t* as = a_slots + (size_t)t * 2 * kABytes;
+              mbar_expect_tx(&afull[t], (uint32_t)(2 * kABytes));
+              tma_load_2d(as, &map_h_hi, &afull[t], g * BK, m0);
+              tma_load_2d(as + kABytes, &map_h_lo, &afull[t], g * BK, m0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      uint32_t wphase = 0, grp = 0;
+      int ws = 0, it = 0;
+      for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+        for (int g = 0; g < G; ++g, ++grp) {
+          const int ksteps = g == G - 1 ? p.ksteps_last : BK / UMMA_K;
+          for (int t = 0; t < T; ++t) {
+            mbar_wait(&wfull[ws], wphase);
+            mbar_wait(&afull[t], grp & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(a_slots + (size_t)t * 2 * kABytes);
+            const uint32_t sw = smem_u32(w_ring + (size_t)ws * 2 * w_bytes);
+            const uint64_t da_hi = make_smem_desc<BK>(sa), da_lo = make_smem_desc<BK>(sa + kABytes);
+            const uint64_t dw_hi = make_smem_desc<BK>(sw), dw_lo = make_smem_desc<BK>(sw + w_bytes);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+              umma_bf16(tmem_d, da_hi + adv, dw_hi + adv, idesc, (g | t | k) ? 1u : 0u);
+              umma_bf16(tmem_d, da_hi + adv, dw_lo + adv, idesc, 1u);
+              umma_bf16(tmem_d, da_lo + adv, dw_hi + adv, idesc, 1u);
+            }
+            if (CS == 1) umma_commit(&wempty[ws]); else umma_commit_mc(&wempty[ws], kMask);
+            umma_commit(&aempty[t]);
+            if (++ws == kNW) { ws = 0; wphase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== edge stager =====================
+    int it = 0;
+    for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
+      const int eb = it & 1;
+      if (it >= 2) mbar_wait_sleep(&eempty[eb], ((it >> 1) - 1) & 1);
+      stage_tile<NI>(etile[eb], p, tg * CS + crank, lane);
+      __syncwarp();
+      mbar_arrive(&efull[eb]);
+    }
+  }
+  } else if (warp >= kFirstAgg) {
+    // ===================== aggregation warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    const int wa = warp - kFirstAgg;
+    uint32_t grp = 0;
+    int it = 0;
+    for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
+      const int eb = it & 1;
+      mbar_wait_sleep(&efull[eb], (it >> 1) & 1);
+      const ETile<NI>& et = etile[eb];
+      for (int g = 0; g < G; ++g, ++grp) {
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+#pragma unroll
+          for (int j = 0; j < NI; ++j) mbar_wait_sleep(&aempty[d * NI + j], (grp & 1) ^ 1);
+          agg_pass<NI>(et, p, d, g, wa, lane, smem_u32(a_slots));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < NI; ++j) mbar_arrive(&afull[d * NI + j]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&eempty[eb]);
+    }
+  } else {
+    // ===================== epilogue =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const bool relu = p.flags & GR_LINEAR_RELU;
+    const int nchunks = p.n_pad / 16;
+    float* s_c = reinterpret_cast<float*>(s_out) + row_in_tile * 16;
+    uint32_t* s_h = reinterpret_cast<uint32_t*>(s_out + BM * 16 * 4) + row_in_tile * 8;
+    uint32_t* s_l = reinterpret_cast<uint32_t*>(s_out + BM * 16 * 4 + BM * 16 * 2) + row_in_tile * 8;
+    const bool issuer = warp == kFirstEpi && lane == 0;
+    int it = 0;
+    for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
+      const int tile = tg * CS + crank;
+      const int acc = it & 1;
+      mbar_wait_sleep(&tmem_full[acc], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = (int64_t)tile * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      float dot = 0.f;
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * 16;
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
+        if (ch == nchunks - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+          const float4 w4 = *reinterpret_cast<const float4*>(s_ws + c0 + j);
+          float x0 = __uint_as_float(r[j]) + b4.x, x1 = __uint_as_float(r[j + 1]) + b4.y;
+          float x2 = __uint_as_float(r[j + 2]) + b4.z, x3 = __uint_as_float(r[j + 3]) + b4.w;
+          if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+          dot = fmaf(x0, w4.x, dot); dot = fmaf(x1, w4.y, dot);
+          dot = fmaf(x2, w4.z, dot); dot = fmaf(x3, w4.w, dot);
+          v[j] = x0; v[j + 1] = x1; v[j + 2] = x2; v[j + 3] = x3;
+        }
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        named_bar_sync(1, kEpiWarps * 32);
+        if (p.C) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(s_c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (p.has_planes) {
+          uint32_t h[8], l[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+            const float2 hf = __bfloat1622float2(h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[j] - hf.x, v[j + 1] - hf.y);
+            h[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+            l[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          *reinterpret_cast<uint4*>(s_h) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(s_h + 4) = make_uint4(h[4], h[5], h[6], h[7]);
+          *reinterpret_cast<uint4*>(s_l) = make_uint4(l[0], l[1], l[2], l[3]);
+          *reinterpret_cast<uint4*>(s_l + 4) = make_uint4(l[4], l[5], l[6], l[7]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(1, kEpiWarps * 32);
+        if (issuer) {
+          const int m0 = tile * BM;
+          if (p.C) tma_store_2d(&map_c, s_out, c0, m0);
+          if (p.has_planes) {
+            tma_store_2d(&map_c_hi, s_out + BM * 16 * 4, c0, m0);
+            tma_store_2d(&map_c_lo, s_out + BM * 16 * 4 + BM * 16 * 2, c0, m0);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (p.dots && row_ok) {
+        p.dots[row] = dot;
+        p.dots[(int64_t)p.M + row] = 0.f;
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CS > 1) cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccStride)
+                 : "memory");
+  }
+}
+
+struct FusedPlan {
+  bool ok;
+  int n_pad, G, ksteps_last;
+  int64_t kp;                 // columns of the pre-formatted W planes
+  size_t w_plane_bytes, smem_bytes;
+};
+
+FusedPlan plan_fused(int64_t Nq, int64_t D, int64_t pitch, int I, int64_t N_out) {
+  FusedPlan f{};
+  f.n_pad = (int)((N_out + 15) / 16 * 16);
+  f.G = (int)((pitch + BK - 1) / BK);
+  f.ksteps_last = (int)((pitch - (int64_t)(f.G - 1) * BK) / UMMA_K);
+  f.kp = (int64_t)f.G * (2 * I + 1) * BK;
+  f.w_plane_bytes = align_up((size_t)N_out * f.kp * 2, 256);
+  f.smem_bytes = I == 2 ? fused_smem_bytes<2>(f.n_pad) : fused_smem_bytes<1>(f.n_pad);
+  f.ok = (I == 1 || I == 2) && Nq >= BM && D >= 8 && D <= pitch && pitch % 16 == 0 && pitch <= kXCols &&
+         N_out >= 8 && N_out <= 256 && f.smem_bytes <= 227 * 1024 && get_encode_fn() != nullptr;
+  return f;
+}
+
+template <int NI, int CS>
+int launch_fused(const CUtensorMap& m_h_hi, const CUtensorMap& m_h_lo, const CUtensorMap& m_w_hi,
+                 const CUtensorMap& m_w_lo, const CUtensorMap& m_c, const CUtensorMap& m_c_hi,
+                 const CUtensorMap& m_c_lo, const FusedPlan& f, const FParams& p, cudaStream_t stream) {
+  static bool attr_done[64] = {};
+  if (first_use_on_device(attr_done)) {
+    GR_CHECK_CUDA(cudaFuncSetAttribute(fused_layer_kernel<NI, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+  }
+  const int ngroups = (p.num_tiles + CS - 1) / CS;
+  const int nclusters = std::max(1, std::min(ngroups, sm_count() / CS));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(nclusters * CS));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = f.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fused_layer_kernel<NI, CS>, m_h_hi, m_h_lo, m_w_hi, m_w_lo, m_c, m_c_hi,
+                                   m_c_lo, p));
+  return GR_OK;
+}
+
+}  // namespace
+}  // namespace gr
+
+extern "C" int gr_fused_layer_supported(int64_t N_nodes, int64_t D, int64_t seg_pitch, int I, int64_t N_out) {
+  return gr::plan_fused(N_nodes, D, seg_pitch, I, N_out).ok ? 1 : 0;
+}
+
+extern "C" size_t gr_fused_layer_workspace_bytes(int64_t D, int64_t seg_pitch, int I, int64_t N_out) {
+  if (D <= 0 || seg_pitch <= 0 || I <= 0 || N_out <= 0) return 0;
+  return 2 * gr::plan_fused(gr::tc::BM, D, seg_pitch, I, N_out).w_plane_bytes;
+}
+
+extern "C" int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
+                              const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
+                              const float* prior, const float* pn_fwd, const float* pn_inv, const float* ins,
+                              const void* h_hi, const void* h_lo, int64_t ldh16, int64_t seg_pitch, const float* W,
+                              int64_t ldw, const float* bias, float* C, int64_t ldc, void* C_hi, void* C_lo,
+                              int64_t ldc16, const float* w_score, float* dots, int B, int N_nodes, int D, int I,
+                              int64_t N_out, int64_t F, uint32_t flags, void* workspace, size_t workspace_bytes,
+                              void* stream_) {
+  using namespace gr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  GR_CHECK_ARG(rowptr_t && rowptr_h && prior && pn_fwd && pn_inv && ins && h_hi && h_lo && W && workspace,
+               "null pointer");
+  GR_CHECK_ARG(F == 0 || (src_t && rel_t && src_h && rel_h), "null edge arrays");
+  GR_CHECK_ARG(C || C_hi, "no output requested");
+  GR_CHECK_ARG(!C_hi || (C_lo && ldc16 >= N_out), "C_lo missing or ldc16 smaller than N_out");
+  GR_CHECK_ARG(!C || ldc >= N_out, "ldc smaller than N_out");
+  GR_CHECK_ARG(!dots || w_score, "dots requested without w_score");
+  GR_CHECK_ARG(B > 0 && N_nodes > 0 && D > 0 && I > 0 && N_out > 0, "sizes must be positive");
+  GR_CHECK_ARG(ldh16 >= seg_pitch && ldh16 % 8 == 0, "ldh16 must be >= seg_pitch and a multiple of 8");
+  GR_CHECK_ARG(ldw >= (int64_t)(2 * I + 1) * D, "ldw smaller than the weight row length");
+  const int64_t M = (int64_t)B * N_nodes;
+  GR_CHECK_ARG(M < (int64_t)0x7fffffff - BM, "B * N exceeds int32 range");
+  FusedPlan f = plan_fused(N_nodes, D, seg_pitch, I, N_out);
+  if (!f.ok) {
+    set_error("gr_fused_layer: unsupported shape N=%d D=%d pitch=%lld I=%d N_out=%lld (need I <= 2, N >= 128, "
+              "pitch %% 16 == 0, pitch <= 256, N_out <= 256 and the stages must fit shared memory)",
+              N_nodes, D, (long long)seg_pitch, I, (long long)N_out);
+    return GR_ERR_UNSUPPORTED;
+  }
+  if (workspace_bytes < 2 * f.w_plane_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("gr_fused_layer: workspace too small or not 256-byte aligned");
+    return GR_ERR_WORKSPACE;
+  }
+  char* ws = reinterpret_cast<char*>(workspace);
+  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + f.w_plane_bytes);
+  if (!(flags & GR_LINEAR_W_PRESPLIT)) {
+    const int64_t work = N_out * f.kp;
+    const int grid = (int)std::min<int64_t>(ceil_div(work, 256), 32LL * sm_count());
+    fused_w_split_kernel<<<grid, 256, 0, stream>>>(W, ldw, (int)N_out, D, I, f.G, w_hi, w_lo);
+    GR_CHECK_LAUNCH();
+  }
+  FParams p{};
+  p.dir[0] = FDir{rowptr_t, src_t, rel_t, w_t, reinterpret_cast<const char*>(pn_fwd)};
+  p.dir[1] = FDir{rowptr_h, src_h, rel_h, w_h, reinterpret_cast<const char*>(pn_inv)};
+  p.prior = prior; p.ins = ins; p.bias = bias; p.C = C; p.ldc = ldc; p.w_score = w_score; p.dots = dots;
+  p.M = (int)M; p.N = (int)N_out; p.n_pad = f.n_pad; p.D = D; p.B = B; p.Nq = N_nodes; p.G = f.G;
+  p.ksteps_last = f.ksteps_last; p.num_tiles = (int)ceil_div(M, BM);
+  p.has_planes = C_hi ? 1 : 0;
+  p.flags = flags;
+  const int cs = ((f.n_pad / 2) % 8 == 0 && p.num_tiles >= 2) ? 2 : 1;
+  CUtensorMap m_h_hi, m_h_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo;
+  // the h planes are exposed with seg_pitch columns only: the box of the last column group is zero filled beyond them
+  if (!make_tmap(&m_h_hi, h_hi, M, seg_pitch, ldh16, BM, BK) || !make_tmap(&m_h_lo, h_lo, M, seg_pitch, ldh16, BM, BK) ||
+      !make_tmap(&m_w_hi, w_hi, N_out, f.kp, f.kp, f.n_pad / cs, BK) ||
+      !make_tmap(&m_w_lo, w_lo, N_out, f.kp, f.kp, f.n_pad / cs, BK)) {
+    set_error("gr_fused_layer: cuTensorMapEncodeTiled failed (plane pointers must be 16-byte aligned)");
+    return GR_ERR_CUDA;
+  }
+  memset(&m_c, 0, sizeof(m_c)); memset(&m_c_hi, 0, sizeof(m_c_hi)); memset(&m_c_lo, 0, sizeof(m_c_lo));
+  bool ok = true;
+  if (C) ok = make_out_tmap(&m_c, C, M, N_out, ldc, 4);
+  const int64_t n16 = std::min<int64_t>((N_out + 15) / 16 * 16, ldc16);
+  if (ok && C_hi) ok = make_out_tmap(&m_c_hi, C_hi, M, n16, ldc16, 2) && make_out_tmap(&m_c_lo, C_lo, M, n16, ldc16, 2);
+  if (!ok) {
+    set_error("gr_fused_layer: output pointers / pitches must be 16-byte aligned (TMA-store epilogue)");
+    return GR_ERR_INVALID_ARG;
+  }
+  if (I == 2) {
+    if (cs == 2) return launch_fused<2, 2>(m_h_hi, m_h_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, f, p, stream);
+    return launch_fused<2, 1>(m_h_hi, m_h_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, f, p, stream);
+  }
+  if (cs == 2) return launch_fused<1, 2>(m_h_hi, m_h_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, f, p, stream);
+  return launch_fused<1, 1>(m_h_hi, m_h_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo, f, p, stream);
+}

@@ -420,6 +420,18 @@ class ReasonGNNLayer(_GraphLayerBase):
             return self._forward_sparse_prior(current_dist, relational_ins, step, need_h)
         tf, ti, pn = self.tables[step]
         wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
+        e2e = getattr(self, "e2e_linear" + str(step))
+        if (self.use_planes and pn is not None and ops.AGG_ABS and ops.FUSED_LAYER and not ops.ACT_BF16
+                and ops.fused_layer_supported(self.N, D, self.Dp, self.num_ins, D)):
+            # aggregation produced straight into the GEMM's operand stages: the neighbour segments never reach HBM
+            sw, sb = self.score_func.weight.view(-1), self.score_func.bias
+            ops.fused_layer(g, current_dist, pn[0], pn[1], relational_ins, self.cur_planes(), self.Dp, e2e.weight,
+                            e2e.bias, out=self.h32 if need_h else None, out_planes=tuple(self.P[1 - self.cur]),
+                            w_score=sw, dots=self.dots, relu=True, w_t=wt, w_h=wh)
+            self.h32_valid = bool(need_h)
+            self.cur = 1 - self.cur
+            dist = ops.masked_softmax(self.dots, sb, self.local_entity_mask, self.B, self.N)
+            return dist, (self.h_view if need_h else None)
         if self.use_planes and pn is not None and ops.AGG_ABS:
             ops.aggregate_dual_abs(g, current_dist, pn[0], pn[1], relational_ins, self.cur_planes(), self.Dp,
                                   self.Dp, wt, wh)

@@ -341,6 +341,42 @@ def aggregate_dual_abs(g, prior, pn_fwd, pn_inv, ins, planes, out_col0, seg_pitc
     STATS.launches += (I + 3) // 4
 
 
+FUSED_LAYER = True      # dense-prior ReaRev layers: aggregation fused into the e2e GEMM (csrc/fused_layer.cu)
+
+
+def fused_layer_supported(N, D, seg_pitch, I, n_out):
+    return bool(_L().gr_fused_layer_supported(N, D, seg_pitch, I, n_out))
+
+
+def fused_layer(g, prior, pn_fwd, pn_inv, ins, h_planes, seg_pitch, W, bias, out=None, out_planes=None,
+                w_score=None, dots=None, relu=True, w_t=None, w_h=None):
+    """One dense-prior ReaRev layer in one kernel (reasongnn.py:134-165): both directions and all instructions are
+    aggregated straight into the tensor-core operand stages of ``relu(e2e([h | nb...]))``.  ``h_planes`` = (hi, lo)
+    bf16 planes whose first ``seg_pitch`` columns hold h; writes any of fp32 ``out``, ``out_planes``, ``dots``."""
+    prior = _cuda(prior, torch.float32, "prior").contiguous()
+    ins = _cuda(ins, torch.float32, "ins").contiguous()
+    B, I, D = ins.shape
+    hi, lo = h_planes
+    n_out = W.shape[0]
+    assert pn_fwd.is_contiguous() and pn_inv.is_contiguous() and hi.stride(0) == lo.stride(0)
+    assert W.stride(1) == 1 and W.shape[1] == (2 * I + 1) * D
+    L = _L()
+    nbytes = L.gr_fused_layer_workspace_bytes(D, seg_pitch, I, n_out)
+    ws, presplit = _weight_ws(W, n_out, W.shape[1], "fused", seg_pitch, nbytes)
+    chi, clo = out_planes if out_planes is not None else (None, None)
+    flags = (LINEAR_RELU if relu else 0) | (LINEAR_W_PRESPLIT if presplit else 0)
+    with _OpTimer("fused_layer"):
+        rc = L.gr_fused_layer(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t),
+                              _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(w_h),
+                              _p(prior), _p(pn_fwd), _p(pn_inv), _p(ins), _p(hi), _p(lo), hi.stride(0), seg_pitch,
+                              _p(W), W.stride(0), _p(bias), _p(out), out.stride(0) if out is not None else 0,
+                              _p(chi), _p(clo), chi.stride(0) if chi is not None else 0, _p(w_score), _p(dots),
+                              B, g.N, D, I, n_out, g.F, flags, _p(ws), ws.numel(), _stream())
+    _lib.check(rc)
+    STATS.launches += 1
+    return out
+
+
 def type_layer(g, table, out, w_t=None, w_h=None, planes=None):
     """out[:, :D] = relu(sum_tail w*table[rel] + sum_head w*table[rel]) (layer_init.py:46-57); optional
     split-bf16 planes of the same values."""

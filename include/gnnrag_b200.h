@@ -204,6 +204,32 @@ int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src_t, const i
  * 64-row tiles, 2 (default) = 9 consumer warps / 72-row tiles, 3 = gather through TMA tile::gather4 copies into
  * shared-memory rings (bit-identical results; slower at cfg2, kept as the measured alternative). */
 
+/* One dense-prior ReaRev layer as ONE kernel (csrc/fused_layer.cu): the aggregation of both directions and all
+ * instructions (reason_layer / reason_layer_inv, reasongnn.py:61-116) is produced straight into the shared-memory
+ * operand slots of the tcgen05 e2e GEMM (torch.cat + e2e_linear + relu, reasongnn.py:158-163; score_func dot :165), so
+ * the 2*I neighbour segments never reach HBM.  Replaces the pair gr_aggregate_dual_abs -> gr_linear_tc_planes.
+ *   h_hi / h_lo    bf16 planes of the layer input h: [B*N, >= seg_pitch] with row stride ldh16 (only the first
+ *                  seg_pitch columns are read; columns D .. seg_pitch-1 must be zero)
+ *   pn_fwd/pn_inv  zero-padded 256-column relation tables of this layer (gr_pad_table256)
+ *   W              e2e_linear weight [N_out, (2I+1)*D] fp32 (row stride ldw); it is re-ordered and split into bf16 hi/lo
+ *                  planes inside `workspace` (gr_fused_layer_workspace_bytes, 256-byte aligned) unless flags carries
+ *                  GR_LINEAR_W_PRESPLIT (workspace kept from an earlier call with the same W)
+ *   outputs        any of C (fp32 [B*N, N_out]), C_hi / C_lo (bf16 planes, row stride ldc16), dots [2*B*N]
+ *                  (dots[m] = <out[m], w_score>, dots[B*N + m] = 0: the layout gr_masked_softmax takes)
+ * Supported (gr_fused_layer_supported): I <= 2, N >= 128, seg_pitch % 16 == 0, seg_pitch <= 256, N_out <= 256 and the
+ * operand stages must fit shared memory (D = N_out = 200 does).  The A operand is bit-identical to the unfused pair;
+ * the tensor core accumulates the k-blocks in a different order (fp32 rounding). */
+int gr_fused_layer_supported(int64_t N_nodes, int64_t D, int64_t seg_pitch, int I, int64_t N_out);
+size_t gr_fused_layer_workspace_bytes(int64_t D, int64_t seg_pitch, int I, int64_t N_out);
+int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
+                   const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
+                   const float* prior, const float* pn_fwd, const float* pn_inv, const float* ins,
+                   const void* h_hi, const void* h_lo, int64_t ldh16, int64_t seg_pitch, const float* W,
+                   int64_t ldw, const float* bias, float* C, int64_t ldc, void* C_hi, void* C_lo,
+                   int64_t ldc16, const float* w_score, float* dots, int B, int N_nodes, int D, int I,
+                   int64_t N_out, int64_t F, uint32_t flags, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 /* Diagnostic only (scripts/agg_probe.py): replays the aggregation kernel's store pattern without any edge work. */
 int gr_debug_store_probe(void* hi, void* lo, int64_t Nt, int64_t ld, int col_start, int ncols, int mode,
                          void* stream);
