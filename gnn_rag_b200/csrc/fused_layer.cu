@@ -109,8 +109,23 @@ __global__ void fused_w_split_kernel(const float* __restrict__ W, int64_t ldw, i
   }
 }
 
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+#ifndef GR_FUSED_WATCHDOG
+#define GR_FUSED_WATCHDOG 1          // debug aid: a wait that lasts > 2 s reports its barrier and traps instead of hanging
+#endif
+
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// `tag` identifies the waiting site in the watchdog report
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, int tag = 0) {
   uint32_t ok = 0;
+#if GR_FUSED_WATCHDOG
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+#endif
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -119,6 +134,17 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
+#if GR_FUSED_WATCHDOG
+    if (!ok && (++spins & 63u) == 0) {
+      const uint64_t t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) {
+        printf("fused_layer watchdog: block %d warp %d lane %d tag %d parity %u\n", (int)blockIdx.x,
+               (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), tag, parity);
+        __trap();
+      }
+    }
+#endif
   }
 }
 
@@ -410,8 +436,9 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // register file: 768 threads x 80 at launch; the control warpgroup (warps 0-3) and the epilogue warpgroup (4-7) hand
-  // registers back so that the four aggregation warpgroups can hold 16 gathers in flight per lane
+  // register file: 768 threads x 80 at launch = the CTA's pool; the control warpgroup (warps 0-3, -> 56) and the epilogue
+  // warpgroup (4-7, -> 72) hand back exactly what the four aggregation warpgroups take (-> 88: 16 gathers in flight per
+  // lane).  setmaxnreg.inc only draws on registers released inside the CTA: 128*56 + 128*72 + 512*88 = 768*80.
   // (the instruction sits at the top of each role's branch: ptxas budgets the code it dominates)
   if (warp < kFirstEpi) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -427,7 +454,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
         for (int g = 0; g < G; ++g, ++grp) {
           for (int t = 0; t < T; ++t) {
             const int kcol = (g * T + t) * BK;
-            mbar_wait(&wempty[ws], wphase ^ 1);
+            mbar_wait_sleep(&wempty[ws], wphase ^ 1, 1);
             uint8_t* st = w_ring + (size_t)ws * 2 * w_bytes;
             mbar_expect_tx(&wfull[ws], (uint32_t)(2 * w_bytes));
             if (CS == 1) {
@@ -439,7 +466,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
             }
             if (++ws == kNW) { ws = 0; wphase ^= 1; }
             if (t == T - 1) {                                      // the h block of this group
-              mbar_wait(&aempty[t], (grp & 1) ^ 1);
+              mbar_wait_sleep(&aempty[t], (grp & 1) ^ 1, 2);
               uint8_t* as = a_slots + (size_t)t * 2 * kABytes;
               mbar_expect_tx(&afull[t], (uint32_t)(2 * kABytes));
               tma_load_2d(as, &map_h_hi, &afull[t], g * BK, m0);
@@ -458,14 +485,14 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
       int ws = 0, it = 0;
       for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
         const int acc = it & 1;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait_sleep(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
         for (int g = 0; g < G; ++g, ++grp) {
           const int ksteps = g == G - 1 ? p.ksteps_last : BK / UMMA_K;
           for (int t = 0; t < T; ++t) {
-            mbar_wait(&wfull[ws], wphase);
-            mbar_wait(&afull[t], grp & 1);
+            mbar_wait_sleep(&wfull[ws], wphase, 4);
+            mbar_wait_sleep(&afull[t], grp & 1, 10 + t);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(a_slots + (size_t)t * 2 * kABytes);
             const uint32_t sw = smem_u32(w_ring + (size_t)ws * 2 * w_bytes);
@@ -490,7 +517,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
     int it = 0;
     for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
       const int eb = it & 1;
-      if (it >= 2) mbar_wait_sleep(&eempty[eb], ((it >> 1) - 1) & 1);
+      if (it >= 2) mbar_wait_sleep(&eempty[eb], ((it >> 1) - 1) & 1, 5);
       stage_tile<NI>(etile[eb], p, tg * CS + crank, lane);
       __syncwarp();
       mbar_arrive(&efull[eb]);
@@ -498,19 +525,19 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
   }
   } else if (warp >= kFirstAgg) {
     // ===================== aggregation warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int wa = warp - kFirstAgg;
     uint32_t grp = 0;
     int it = 0;
     for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
       const int eb = it & 1;
-      mbar_wait_sleep(&efull[eb], (it >> 1) & 1);
+      mbar_wait_sleep(&efull[eb], (it >> 1) & 1, 6);
       const ETile<NI>& et = etile[eb];
       for (int g = 0; g < G; ++g, ++grp) {
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
 #pragma unroll
-          for (int j = 0; j < NI; ++j) mbar_wait_sleep(&aempty[d * NI + j], (grp & 1) ^ 1);
+          for (int j = 0; j < NI; ++j) mbar_wait_sleep(&aempty[d * NI + j], (grp & 1) ^ 1, 20 + d * NI + j);
           agg_pass<NI>(et, p, d, g, wa, lane, smem_u32(a_slots));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -538,7 +565,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
     for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
       const int tile = tg * CS + crank;
       const int acc = it & 1;
-      mbar_wait_sleep(&tmem_full[acc], (it >> 1) & 1);
+      mbar_wait_sleep(&tmem_full[acc], (it >> 1) & 1, 7);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row = (int64_t)tile * BM + row_in_tile;
       const bool row_ok = row < p.M;
@@ -644,6 +671,17 @@ int launch_fused(const CUtensorMap& m_h_hi, const CUtensorMap& m_h_lo, const CUt
   if (first_use_on_device(attr_done)) {
     GR_CHECK_CUDA(cudaFuncSetAttribute(fused_layer_kernel<NI, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
+  }
+  // the setmaxnreg budget of the kernel (56 / 72 / 88) redistributes exactly 768 x 80 registers
+  static int num_regs = 0;
+  if (num_regs == 0) {
+    cudaFuncAttributes fa{};
+    GR_CHECK_CUDA(cudaFuncGetAttributes(&fa, fused_layer_kernel<NI, CS>));
+    num_regs = fa.numRegs;
+  }
+  if (num_regs != 80) {
+    set_error("gr_fused_layer: kernel was compiled with %d registers per thread, the warp-group budget needs 80", num_regs);
+    return GR_ERR_UNSUPPORTED;
   }
   const int ngroups = (p.num_tiles + CS - 1) / CS;
   const int nclusters = std::max(1, std::min(ngroups, sm_count() / CS));
