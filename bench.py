@@ -78,6 +78,8 @@ def parse():
     ap.add_argument("--act-bf16", type=int, default=None,
                     help="1: bf16 activation storage (hi plane only, one-product GEMM); default: on for cfg3 "
                          "(BASELINE configs[2] names bf16), off elsewhere")
+    ap.add_argument("--fused", type=int, default=1,
+                    help="0: dense-prior layers as aggregation kernel + GEMM instead of the fused layer kernel")
     ap.add_argument("--cuda-graph", type=int, default=1,
                     help="1: run the step through gnn_rag_b200.GraphedStep (CUDA-graph replay over static buffers)")
     return ap.parse_args()
@@ -273,6 +275,7 @@ def run_ours(a):
         ops.set_option("tc_cluster", a.tc_cluster)
     act_bf16 = bool(a.act_bf16) if a.act_bf16 is not None else (a.config == "cfg3")
     ops.ACT_BF16 = act_bf16
+    ops.FUSED_LAYER = bool(a.fused)
     c = per_gpu_config(a.config)
     B, N, D, I = c["B"], c["N"], c["D"], c["I"]
     args = model_args_for(c, True)
@@ -322,30 +325,41 @@ def run_ours(a):
     # ---- eager replica of the timed region: per-launch CUDA events around every aggregation launch (the
     # live roofline measurement) and the launch count; with --cuda-graph the same kernels are replayed from the
     # graph in the timed region below, where per-launch events cannot be recorded
-    ops.STATS.reset()
-    ops.STATS.time_agg = True
-    ops.STATS.time_ops = True
-    rep_evs = []
-    for _ in range(a.steps):
-        flush.fill_(1)
-        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        step_eager(dev_batch)
-        e0.record()
-        rep_evs.append((s0, e0))
-    barrier()
-    ops.STATS.time_agg = False
-    ops.STATS.time_ops = False
-    launches = ops.STATS.launches
-    agg = [(s.elapsed_time(e), tag) for s, e, tag in ops.STATS.agg_events]
-    # per-kernel-class device time of the eager replica (events around every wrapper, on the launching stream)
-    op_ms, gemm = {}, {}
-    for s_, e_, cls, info in ops.STATS.op_events:
-        ms = s_.elapsed_time(e_)
-        op_ms[cls] = op_ms.get(cls, 0.0) + ms
-        if cls == "gemm_tc":
-            gemm.setdefault(info, []).append(ms)
-    rep_ms = sum(s_.elapsed_time(e_) for s_, e_ in rep_evs)
+    def replica(nsteps):
+        ops.STATS.reset()
+        ops.STATS.time_agg = True
+        ops.STATS.time_ops = True
+        evs_ = []
+        for _ in range(nsteps):
+            flush.fill_(1)
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            step_eager(dev_batch)
+            e0.record()
+            evs_.append((s0, e0))
+        barrier()
+        ops.STATS.time_agg = False
+        ops.STATS.time_ops = False
+        agg_ = [(s.elapsed_time(e), tag) for s, e, tag in ops.STATS.agg_events]
+        # per-kernel-class device time of the eager replica (events around every wrapper, on the launching stream)
+        op_ms_, gemm_, fused_ = {}, {}, []
+        for s_, e_, cls, info in ops.STATS.op_events:
+            ms = s_.elapsed_time(e_)
+            op_ms_[cls] = op_ms_.get(cls, 0.0) + ms
+            if cls == "gemm_tc":
+                gemm_.setdefault(info, []).append(ms)
+            if cls == "fused_layer":
+                fused_.append(ms)
+        return (ops.STATS.launches, agg_, op_ms_, gemm_, fused_,
+                sum(s_.elapsed_time(e_) for s_, e_ in evs_), nsteps)
+
+    launches, agg, op_ms, gemm, fused_ms, rep_ms, agg_steps = replica(a.steps)
+    if fused_ms:
+        # the unfused pair stays the roofline unit of the aggregation kernel and of the K = (2I+1)D GEMM: a second
+        # replica with the fused layer kernel switched off supplies `roofline` / `roofline_gemm`
+        ops.FUSED_LAYER = False
+        _l, agg, _o, gemm, _f, _r, agg_steps = replica(min(a.steps, 10))
+        ops.FUSED_LAYER = True
     for _ in range(3):
         step(dev_batch)
     barrier()
@@ -453,7 +467,7 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    per_step = len(agg) // max(a.steps, 1)
+    per_step = len(agg) // max(agg_steps, 1)
     # layer 0 of every iteration sees the one-hot seed prior.  With the sparse-prior fast path (default) that layer
     # never reaches the aggregation kernel (K = D GEMM + frontier fix-up), so every timed launch is a dense-prior
     # launch; without it those launches are pure output writes and are reported separately.
@@ -482,7 +496,8 @@ def run_ours(a):
                 "launches_per_step": per_step,
                 "measured_in": "eager replica of the timed region (same process, same inputs, L2 flushed)",
                 "seed_prior_launch_ms": float(np.mean(seedl)) if seedl else None,
-                "agg_share_of_step": (sum(ms for ms, _ in agg) / dev_ms) if dev_ms else None}
+                "agg_share_of_step": ((sum(ms for ms, _ in agg) / max(agg_steps, 1)) / (dev_ms / a.steps))
+                if (dev_ms and not fused_ms) else None}
     # ---- tensor-core GEMM roofline (the largest e2e GEMM of the step) and the share table ---------------------
     roofline_gemm = None
     if gemm:
@@ -497,8 +512,25 @@ def run_ours(a):
                          "peak": tf_peak, "unit": "TFLOP/s", "frac": flops / (g_ms * 1e-3) / 1e12 / tf_peak,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, of measured)" if "bf16_tflops" in peaks
                          else "1590 TFLOP/s (of fallback)",
-                         "avg_launch_ms": g_ms, "launches_per_step": len(ts) // max(a.steps, 1),
+                         "avg_launch_ms": g_ms, "launches_per_step": len(ts) // max(agg_steps, 1),
                          "fp32_equivalent_tflops": 2.0 * gM * gN * gK / (g_ms * 1e-3) / 1e12}
+    roofline_fused = None
+    if fused_ms:
+        f_ms = float(np.mean(fused_ms))
+        Kd = (2 * I + 1) * D
+        flops = 3 * 2.0 * B * N * D * Kd
+        tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+        # what the fused kernel has to move: both CSRs + prior, the relation tables, h planes in, h planes out
+        fbytes = 2 * F * 8 + 2 * (B * N + 1) * 4 + B * N * 4 + 2 * R1 * D * 4 + B * I * D * 4 + 2 * B * N * D * 4
+        roofline_fused = {"bound": "tensor", "kernel": "fused_layer_kernel (gr_fused_layer: aggregation -> tcgen05 GEMM)",
+                          "achieved": flops / (f_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                          "frac": flops / (f_ms * 1e-3) / 1e12 / tf_peak, "avg_launch_ms": f_ms,
+                          "launches_per_step": len(fused_ms) // max(a.steps, 1),
+                          "replaces_ms": (dense_ms + roofline_gemm["avg_launch_ms"]) if roofline_gemm else None,
+                          "algorithmic_hbm_bytes_per_launch": int(fbytes),
+                          "hbm_gbs": fbytes / (f_ms * 1e-3) / 1e9}
+        roofline["measured_in"] = ("second eager replica with the fused layer kernel switched off (the timed step runs "
+                                   "the fused kernel; the unfused pair is the roofline unit of the aggregation)")
     shares = {k: v / rep_ms for k, v in sorted(op_ms.items(), key=lambda kv: -kv[1])} if rep_ms else {}
     shares["_note"] = ("device time per kernel class / eager step time, from CUDA events around every wrapper in the "
                        "eager replica (the question side runs on a second stream and overlaps: shares can sum past 1)")
@@ -510,7 +542,7 @@ def run_ours(a):
             "config": config_dict(a.config, c, world=world, extra={
                 "global_questions": world * B, "l2": "256 MiB flush write between timed steps",
                 "timing": "CUDA events per step on the launch stream, max over ranks",
-                "cuda_graph": bool(a.cuda_graph),
+                "cuda_graph": bool(a.cuda_graph), "fused_layer_kernel": bool(fused_ms),
                 "wall_s_timed_region_incl_flush": wall}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps, "mode": e2e_mode,
@@ -522,7 +554,7 @@ def run_ours(a):
                                 "distributions): host casts + H2D + graph + D2H inside the timed region"}},
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches // max(a.steps, 1)), "clocks": clocks,
             "roofline": roofline,
-            "roofline_gemm": roofline_gemm, "shares": shares}
+            "roofline_gemm": roofline_gemm, "roofline_fused": roofline_fused, "shares": shares}
     if not a.no_cpu_baseline and world == 1:
         sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
         nq = min(a.cpu_sample if a.cpu_sample else {"cfg3": 1, "cfg5": 1}.get(a.config, 8), B)

@@ -42,12 +42,17 @@ SIGNATURES = {
     "gr_aggregate_dual_abs": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p,
                                      c_f32p, c_f32p, c_f32p, c_i64, c_f32p, c_void_p, c_void_p, c_i64, c_i64, c_i64,
                                      c_int, c_int, c_int, c_int, c_i64, c_i32p, c_void_p]),
+    "gr_fused_profile_read": (c_int, [c_void_p, c_int]),
     "gr_fused_layer_supported": (c_int, [c_i64, c_i64, c_i64, c_int, c_i64]),
     "gr_fused_layer_workspace_bytes": (c_size, [c_i64, c_i64, c_int, c_i64]),
     "gr_fused_layer": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_void_p, c_void_p, c_i64, c_i64, c_f32p,
                                c_i64, c_f32p, c_f32p, c_i64, c_void_p, c_void_p, c_i64, c_f32p, c_f32p,
-                               c_int, c_int, c_int, c_int, c_i64, c_i64, c_u32, c_void_p, c_size, c_void_p]),
+                               c_int, c_int, c_int, c_int, c_i64, c_i64, c_u32, c_void_p, c_size, c_void_p, c_size,
+                               c_void_p]),
+    "gr_fused_ell_bytes": (c_size, [c_int, c_int, c_i64]),
+    "gr_fused_ell_build": (c_int, [c_i32p, c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_i32p, c_f32p, c_int, c_int, c_i64,
+                                   c_void_p, c_size, c_void_p]),
     "gr_debug_store_probe": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_void_p]),
     "gr_type_layer": (c_int, [c_i32p, c_i32p, c_f32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_i64,
                               c_void_p, c_void_p, c_i64,

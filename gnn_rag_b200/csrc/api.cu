@@ -32,6 +32,7 @@ extern int g_tc_cluster;
 extern int g_tc_bk;
 extern int g_tc_tma_store;
 extern int g_opt_agg_abs_ws;
+extern int g_fused_debug;
 
 int linear_simt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                 const float* addend, int64_t ld_addend, int64_t addend_rows, float* C, int64_t ldc,
@@ -52,6 +53,7 @@ extern "C" int gr_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_bk")) { g_tc_bk = (int)value; return GR_OK; }
   if (!strcmp(name, "tc_tma_store")) { g_tc_tma_store = (int)value; return GR_OK; }
   if (!strcmp(name, "agg_abs_ws")) { g_opt_agg_abs_ws = (int)value; return GR_OK; }
+  if (!strcmp(name, "fused_debug")) { g_fused_debug = (int)value; return GR_OK; }
   set_error("gr_set_option: unknown option '%s'", name);
   return GR_ERR_INVALID_ARG;
 }

@@ -9,7 +9,7 @@
 // SWIZZLE_64B, bf16 hi/lo planes -- the layout TMA would have written), only the h segment and W come from memory.
 //
 // Per 128-row tile the K dimension is walked in G column groups of 32; group g holds, in this order,
-//     Y(dir 0, j = 0..I-1), Y(dir 1, j = 0..I-1), H              (T = 2*I + 1 k-blocks of 32 columns)
+//     H, Y(dir 0, j = 0..I-1), Y(dir 1, j = 0..I-1)              (T = 2*I + 1 k-blocks of 32 columns)
 // i.e. column block g of every segment of [h | nb_0^fwd | nb_0^inv | nb_1^fwd | ...].  The S = sum c*v / Q = sum c*|v|
 // accumulation of aggregate_abs.cu is instruction independent, so one pass over a row's in-edges restricted to the 32
 // columns of group g yields the I blocks Y(dir, 0..I-1) together.  W is pre-formatted once per weight version in this
@@ -35,6 +35,18 @@
 #include "tcgen05.cuh"
 
 namespace gr {
+
+// gr_set_option("fused_debug", bits): timing decomposition of the fused kernel (results are WRONG with any bit set).
+// 1: aggregation warps skip the gather / emit work; 2: the stager skips the edge staging; 4: the epilogue skips its stores
+int g_fused_debug = 0;
+
+// bit 32 of fused_debug: per-CTA cycle counters of every role's waits (gr_fused_profile_read), 16 slots per CTA:
+// 0 MMA loop total, 1 MMA wait W, 2 MMA wait aggregated operand, 3 MMA wait h operand, 4 MMA wait accumulator,
+// 5 producer wait W slot, 6 producer wait h slot, 7 aggregation warp 0 total, 8 its wait for operand slots, 9 its wait
+// for the tile descriptor, 10 its aggregation work, 11 stager (direction 0) wait for a descriptor buffer, 12 its staging
+// work, 13 epilogue warp 0 wait for the accumulator, 14 epilogue total
+__device__ unsigned long long g_fused_prof[160 * 16];
+
 namespace {
 
 using namespace tc;
@@ -60,8 +72,27 @@ struct FDir {
   const char* pn;          // zero-padded relation table [R1, 256] fp32
 };
 
+// Slot-major "quad ELL" form of both CSRs, built ONCE per batch (fused_ell_build_kernel): for every 128-row tile and
+// direction a block of entries, quad Q (4 consecutive rows) owning m_Q = max in-degree of its rows slots, slot k of row r
+// at block offset qoff[Q] + 4k + r.  Static per batch: source node, relation table byte offset and edge weight of every
+// entry (padding entries: node 0, offset 0, weight 0).  Per layer one streaming pass (fused_coef_kernel) turns them into
+// {offset, c_f = w (w prior[src])} pairs, which the fused kernel's stager moves into shared memory with one bulk copy
+// per tile and direction -- no per-layer index arithmetic, no dependent gathers inside the fused kernel.
+constexpr int kQRow = BM / 4 + 4;     // per (direction, tile): 32 quad offsets, [32] = entries of the tile, [33] = block base
+struct EllView {
+  int32_t* counters;                  // [2] entries allocated per direction (atomic bump allocator of the build)
+  int32_t* qrow;                      // [2][ntiles][kQRow]
+  int32_t* src;                       // [2][cap]
+  uint32_t* off;                      // [2][cap]
+  float* w;                           // [2][cap]
+  int2* rc;                           // [2][cap] per-layer {off, c}
+  int64_t cap;
+  int ntiles;
+};
+
 struct FParams {
   FDir dir[2];
+  EllView ell;
   const float* prior;      // [Nt]
   const float* ins;        // [B, I, D]
   const float* bias;
@@ -72,14 +103,22 @@ struct FParams {
   int M, N, n_pad, D, B, Nq, G, ksteps_last, num_tiles;
   int has_planes;
   uint32_t flags;
+  int debug;
 };
 
+// Tile descriptor the edge stager hands to the aggregation warps.  The in-edges are staged SLOT-MAJOR per quad of 4
+// consecutive rows: quad Q (rows 4Q .. 4Q+3) owns m_Q = max in-degree of its rows slots; slot k of row r sits at entry
+// qbase[Q] + 4k + r and is {table byte offset rel * 1024, c_f}, or {0, 0} when row r has fewer than k+1 in-edges (a
+// gather of table row 0 weighted by zero).  A quarter-warp (8 lanes x 4 columns) owns a row, one warp-wide 16-byte load
+// gathers one in-edge of each row of the quad, and the loop over slots has a warp-uniform trip count with no predicates.
 template <int NI>
 struct alignas(16) ETile {
-  int2 rc[2][kECap];                  // {table byte offset rel * 1024, float_as_int(c_f)}
+  int2 rc[2][kECap];
   float x[2][NI][kXCols];             // raw instruction vectors of the tile's two questions
-  int32_t rowptr[2][BM + 4];          // global edge indices
-  int32_t nrows, lr_switch, pad_[2];
+  int32_t rowptr[2][BM + 4];          // global edge indices (slow path, and the stager's own row lookup)
+  int32_t qbase[2][kQRow];            // entry offset of each quad's block, [BM/4] = total entries (bulk copy of the ELL row)
+  int32_t nrows, lr_switch, fits[2];
+  int2 zero_entry[2];                 // {0, 0}: what the slots beyond a quad's block read (c = 0: contributes nothing)
 };
 
 template <int NI>
@@ -99,8 +138,8 @@ __global__ void fused_w_split_kernel(const float* __restrict__ W, int64_t ldw, i
     const int k = (int)(i - n * Kp);
     const int blk = k / BK, c = k % BK;
     const int g = blk / T, t = blk % T;
-    // t < 2I: Y(dir = t / I, j = t % I) -> segment 1 + 2j + dir;  t == 2I: the h segment
-    const int seg = t == 2 * I ? 0 : 1 + 2 * (t % I) + t / I;
+    // t == 0: the h segment;  t >= 1: Y(dir = (t-1) / I, j = (t-1) % I) -> segment 1 + 2j + dir
+    const int seg = t == 0 ? 0 : 1 + 2 * ((t - 1) % I) + (t - 1) / I;
     const int col = g * BK + c;
     const float v = col < D ? __ldg(W + n * ldw + (int64_t)seg * D + col) : 0.f;
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -110,7 +149,7 @@ __global__ void fused_w_split_kernel(const float* __restrict__ W, int64_t ldw, i
 }
 
 #ifndef GR_FUSED_WATCHDOG
-#define GR_FUSED_WATCHDOG 1          // debug aid: a wait that lasts > 2 s reports its barrier and traps instead of hanging
+#define GR_FUSED_WATCHDOG 0          // debug aid: a wait that lasts > 2 s reports its barrier and traps instead of hanging
 #endif
 
 __device__ __forceinline__ uint64_t global_ns() {
@@ -120,7 +159,32 @@ __device__ __forceinline__ uint64_t global_ns() {
 }
 
 // `tag` identifies the waiting site in the watchdog report
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, int tag = 0) {
+#ifndef GR_FUSED_PROFILE
+#define GR_FUSED_PROFILE 0           // 1: compile the per-role wait-cycle counters in (fused_debug bit 32; costs registers)
+#endif
+struct Prof {                                   // cycle accumulation for one role (only when debug bit 32 is set)
+#if GR_FUSED_PROFILE
+  bool on;
+  long long acc[4];
+  __device__ __forceinline__ void init(bool enable) { on = enable; acc[0] = acc[1] = acc[2] = acc[3] = 0; }
+  __device__ __forceinline__ long long t() const { return on ? clock64() : 0; }
+  __device__ __forceinline__ void add(int i, long long t0) { if (on) acc[i] += clock64() - t0; }
+  __device__ __forceinline__ void store(int slot0, int n) const {
+    if (on) for (int i = 0; i < n; ++i) g_fused_prof[(blockIdx.x % 160) * 16 + slot0 + i] = (unsigned long long)acc[i];
+  }
+  __device__ __forceinline__ void total(int slot, long long t0) const {
+    if (on) g_fused_prof[(blockIdx.x % 160) * 16 + slot] = (unsigned long long)(clock64() - t0);
+  }
+#else
+  __device__ __forceinline__ void init(bool) {}
+  __device__ __forceinline__ long long t() const { return 0; }
+  __device__ __forceinline__ void add(int, long long) {}
+  __device__ __forceinline__ void store(int, int) const {}
+  __device__ __forceinline__ void total(int, long long) const {}
+#endif
+};
+
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, int tag = 0, unsigned backoff_ns = 0) {
   uint32_t ok = 0;
 #if GR_FUSED_WATCHDOG
   uint64_t t0 = 0;
@@ -134,8 +198,11 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
+    // the hardware suspend returns after ~100 cycles whatever the hint says: back off explicitly so that waiting roles
+    // do not spend the issue slots the working warps need
+    if (!ok && backoff_ns) __nanosleep(backoff_ns);
 #if GR_FUSED_WATCHDOG
-    if (!ok && (++spins & 63u) == 0) {
+    if (!ok && (++spins & 1023u) == 0) {
       const uint64_t t = global_ns();
       if (t0 == 0) t0 = t;
       else if (t - t0 > 2000000000ull) {
@@ -148,6 +215,14 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
   }
 }
 
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ float2 ldg2(const char* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 // explicit shared-state-space accesses (the carve-up of the dynamic buffer goes through integer alignment, after
 // which the compiler would fall back to generic loads / stores)
@@ -173,206 +248,180 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
 // ---------------------------------------------------------------------------------------------------------
 // edge stager (one warp): tile descriptor of tile `tile` into `et`
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Stager warp `d` (0: also the tile header and the instruction vectors) fills direction d of the tile descriptor: the
+// quad offsets and the tile's {offset, c} entries are bulk-copied from the per-layer ELL arrays; completion is counted
+// on the descriptor's full barrier (expect_tx), on which lane 0 arrives once for the warp.
 template <int NI>
-__device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int tile, int lane) {
+__device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int tile, int lane, int d, uint64_t* full) {
   const int64_t r0 = (int64_t)tile * BM;
   const int nrows = tile < p.num_tiles ? (int)min((int64_t)BM, (int64_t)p.M - r0) : 0;
+  int total = 0, base = 0;
+  if (nrows > 0 && lane == 0) {
+    const int32_t* qr = p.ell.qrow + ((int64_t)d * p.ell.ntiles + tile) * kQRow;
+    total = __ldg(qr + BM / 4);
+    base = __ldg(qr + BM / 4 + 1);
+  }
+  total = __shfl_sync(0xffffffffu, total, 0);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const bool fits = total <= kECap && base >= 0 && !(p.debug & 2);
   if (lane == 0) {
-    et.nrows = nrows;
-    const int b0 = nrows > 0 ? (int)(r0 / p.Nq) : 0;
-    et.lr_switch = p.Nq - (int)(r0 - (int64_t)b0 * p.Nq);       // first tile row of question b0 + 1 (Nq >= BM)
-  }
-  if (nrows == 0) return;
-  const int b0 = (int)(r0 / p.Nq);
-  int eb[2], ne[2];
-#pragma unroll
-  for (int d = 0; d < 2; ++d) {
-    const int32_t* rp = p.dir[d].rowptr + r0;
-    const int e0 = __ldg(rp), e1 = __ldg(rp + nrows);
-#pragma unroll
-    for (int k = 0; k < (BM + 32) / 32; ++k) {
-      const int i = lane + 32 * k;
-      if (i <= nrows) et.rowptr[d][i] = __ldg(rp + i);
+    et.fits[d] = fits ? 1 : 0;
+    if (d == 0) {
+      et.nrows = nrows;
+      const int b0 = nrows > 0 ? (int)(r0 / p.Nq) : 0;
+      et.lr_switch = p.Nq - (int)(r0 - (int64_t)b0 * p.Nq);       // first tile row of question b0 + 1 (Nq >= BM)
+      et.zero_entry[0] = make_int2(0, 0);
     }
-    eb[d] = e0;
-    ne[d] = min(e1 - e0, kECap);
   }
-  for (int i = lane; i < 2 * NI * kXCols; i += 32) {
-    const int c = i % kXCols, j = (i / kXCols) % NI, q = i / (kXCols * NI);
-    const int b = b0 + q;
-    (&et.x[0][0][0])[i] = (c < p.D && b < p.B) ? __ldg(p.ins + ((int64_t)b * NI + j) * p.D + c) : 0.f;
-  }
-#pragma unroll
-  for (int d = 0; d < 2; ++d) {
-    const FDir& dd = p.dir[d];
-    for (int i0 = 0; i0 < ne[d]; i0 += 128) {
-      int sidx[4], ridx[4];
-      float wv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + lane + 32 * u;
-        const bool ok = i < ne[d];
-        sidx[u] = ok ? __ldg(dd.src + eb[d] + i) : 0;
-        ridx[u] = ok ? __ldg(dd.rel + eb[d] + i) : 0;
-        wv[u] = (ok && dd.w) ? __ldg(dd.w + eb[d] + i) : 1.0f;
+  uint32_t tx = 0;
+  if (nrows > 0) {
+    if (d == 0) {
+      const int b0 = (int)(r0 / p.Nq);
+      for (int i = lane; i < 2 * NI * kXCols; i += 32) {
+        const int c = i % kXCols, j = (i / kXCols) % NI, q = i / (kXCols * NI);
+        const int b = b0 + q;
+        (&et.x[0][0][0])[i] = (c < p.D && b < p.B) ? __ldg(p.ins + ((int64_t)b * NI + j) * p.D + c) : 0.f;
       }
-      float pr[4];
+    }
+    if (!fits) {
+      // slow path of this tile / direction: the aggregation warps walk the CSR themselves, they need the row pointers
+      const int32_t* rp = p.dir[d].rowptr + r0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) pr[u] = __ldg(p.prior + sidx[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + lane + 32 * u;
-        if (i < ne[d])
-          et.rc[d][i] = make_int2((int)((uint32_t)ridx[u] * (uint32_t)kPnRowBytes),
-                                  __float_as_int(wv[u] * (wv[u] * pr[u])));             // reasongnn.py:80-84
+      for (int k = 0; k < (BM + 32) / 32; ++k) {
+        const int i = lane + 32 * k;
+        if (i <= BM) et.rowptr[d][i] = __ldg(rp + min(i, nrows));
       }
     }
   }
+  __syncwarp();                                                  // the lanes' descriptor stores precede lane 0's arrival
+  if (lane == 0 && nrows > 0 && fits) {
+    const int32_t* qr = p.ell.qrow + ((int64_t)d * p.ell.ntiles + tile) * kQRow;
+    tx = (uint32_t)(kQRow * 4) + (uint32_t)total * 8u;
+    mbar_expect_tx(full, tx);
+    bulk_g2s(smem_u32(&et.qbase[d][0]), qr, (uint32_t)(kQRow * 4), full);
+    if (total > 0) bulk_g2s(smem_u32(&et.rc[d][0]), p.ell.rc + (int64_t)d * p.ell.cap + base, (uint32_t)total * 8u, full);
+  }
+  if (lane == 0 && tx == 0) mbar_arrive(full);                   // (with tx > 0 the expect_tx above was the arrival)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// aggregation: one pass = (direction d, column group g) for this warp's 8 rows -> I A-operand blocks
+// aggregation: one pass = (direction d, column group g) for this warp's 8 rows (2 quads) -> I A-operand blocks
 // ---------------------------------------------------------------------------------------------------------
-// y = xp * (Q + S) + xn * (Q - S)  (xp = relu(x)/2, xn = relu(-x)/2), split into bf16 hi / lo, stored at the (row, column
-// pair) slot of the K-major SWIZZLE_64B operand tile: 16-byte chunk index XOR ((row >> 1) & 3)
-__device__ __forceinline__ void emit_pair(uint32_t slot, float2 xp, float2 xn, float2 U, float2 V) {
-  float2 y = __fmul2_rn(xp, U);
-  y = __ffma2_rn(xn, V, y);
-  const __nv_bfloat162 h = __floats2bfloat162_rn(y.x, y.y);
-  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
-  const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-  const float2 r = __ffma2_rn(f, make_float2(-1.f, -1.f), y);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(r.x, r.y);
-  sts_u32(slot, u);
-  sts_u32(slot + kABytes, *reinterpret_cast<const uint32_t*>(&l));
+__device__ __forceinline__ float4 ldg4(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
 
-// one gather slot: if (k < rem) { {off, c} = staged edge; v = table[off + lane columns] }.  One asm block per slot keeps
-// the per-slot cost at four instructions (ISETP, LDS, IMAD.WIDE, LDG.64) and lets the 16 slots of a round issue
-// back to back; the outputs keep their old value when the slot is off (the matching FMAs are predicated the same way)
-__device__ __forceinline__ void gather_slot(float2& v, uint32_t edge_s, int rem, int k, const char* tb) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t.reg .u32 o;\n\t.reg .u64 a;\n\t"
-      "setp.gt.s32 q, %2, %3;\n\t"
-      "ld.shared.b32 o, [%4];\n\t"          // unconditional: the address always lies inside the tile descriptor
-      "mad.wide.u32 a, o, 1, %5;\n\t"
-      "@q ld.global.nc.v2.f32 {%0, %1}, [a];\n\t}"
-      : "+f"(v.x), "+f"(v.y)
-      : "r"(rem), "r"(k), "r"(edge_s), "l"(tb));
-}
-
-template <int NI>
-struct LaneX {                      // relu(+-x)/2 of one question at this lane's two columns of the group
-  float2 xp[NI], xn[NI];
-  __device__ __forceinline__ void load(uint32_t xs) {          // xs = smem address of x[q][0][col]
-#pragma unroll
-    for (int j = 0; j < NI; ++j) {
-      const float2 x = lds_f2(xs + (uint32_t)(j * kXCols * 4));
-      xp[j] = make_float2(0.5f * fmaxf(x.x, 0.f), 0.5f * fmaxf(x.y, 0.f));
-      xn[j] = make_float2(0.5f * fmaxf(-x.x, 0.f), 0.5f * fmaxf(-x.y, 0.f));
-    }
+struct Acc4 {                                   // S = sum c*v, Q = sum c*|v| for this lane's 4 columns
+  float2 s0, s1, q0, q1;
+  __device__ __forceinline__ void clear() { s0 = s1 = q0 = q1 = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void add(float c, const float4& v) {
+    const float2 cc = make_float2(c, c);
+    s0 = __ffma2_rn(cc, make_float2(v.x, v.y), s0);
+    s1 = __ffma2_rn(cc, make_float2(v.z, v.w), s1);
+    q0 = __ffma2_rn(cc, make_float2(fabsf(v.x), fabsf(v.y)), q0);
+    q1 = __ffma2_rn(cc, make_float2(fabsf(v.z), fabsf(v.w)), q1);
   }
 };
+
+// y = xp * (Q + S) + xn * (Q - S) for 4 columns (xp = relu(x)/2, xn = relu(-x)/2), split into bf16 hi / lo, 8-byte
+// stores into the K-major SWIZZLE_64B operand tile
+__device__ __forceinline__ void emit_quad(uint32_t slot, const float4& x, const float2& U0, const float2& U1,
+                                          const float2& V0, const float2& V1) {
+  const float2 xp0 = make_float2(0.5f * fmaxf(x.x, 0.f), 0.5f * fmaxf(x.y, 0.f));
+  const float2 xp1 = make_float2(0.5f * fmaxf(x.z, 0.f), 0.5f * fmaxf(x.w, 0.f));
+  const float2 xn0 = make_float2(0.5f * fmaxf(-x.x, 0.f), 0.5f * fmaxf(-x.y, 0.f));
+  const float2 xn1 = make_float2(0.5f * fmaxf(-x.z, 0.f), 0.5f * fmaxf(-x.w, 0.f));
+  float2 y0 = __fmul2_rn(xp0, U0), y1 = __fmul2_rn(xp1, U1);
+  y0 = __ffma2_rn(xn0, V0, y0);
+  y1 = __ffma2_rn(xn1, V1, y1);
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(y0.x, y0.y), h1 = __floats2bfloat162_rn(y1.x, y1.y);
+  const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+  const float2 f0 = make_float2(__uint_as_float(u0 << 16), __uint_as_float(u0 & 0xffff0000u));
+  const float2 f1 = make_float2(__uint_as_float(u1 << 16), __uint_as_float(u1 & 0xffff0000u));
+  const float2 m1 = make_float2(-1.f, -1.f);
+  const float2 r0 = __ffma2_rn(f0, m1, y0), r1 = __ffma2_rn(f1, m1, y1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(r0.x, r0.y), l1 = __floats2bfloat162_rn(r1.x, r1.y);
+  sts_u2(slot, u0, u1);
+  sts_u2(slot + kABytes, *reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
 
 template <int NI>
 __device__ __forceinline__ void agg_pass(const ETile<NI>& et, const FParams& p, int d, int g, int wa, int lane,
                                          uint32_t a_slots) {
-  const int hw = lane >> 4, l16 = lane & 15;
+  const int r = lane >> 3, c8 = lane & 7;                    // row of the quad, 4-column group of the 32-column block
   const uint32_t et_s = smem_u32(&et);
-  const uint32_t rp_s = et_s + (uint32_t)offsetof(ETile<NI>, rowptr) + (uint32_t)d * (BM + 4) * 4u;
   const int nrows = (int)lds_u32(et_s + (uint32_t)offsetof(ETile<NI>, nrows));
   const int lr_switch = (int)lds_u32(et_s + (uint32_t)offsetof(ETile<NI>, lr_switch));
+  const bool fits = lds_u32(et_s + (uint32_t)offsetof(ETile<NI>, fits) + (uint32_t)d * 4u) != 0;
   const FDir& dd = p.dir[d];
-  const char* tb = dd.pn + (g * BK + 2 * l16) * 4;
-  const int ebase = (int)lds_u32(rp_s);
-  const bool fits = (int)lds_u32(rp_s + (uint32_t)nrows * 4u) - ebase <= kECap;     // warp uniform
-  const uint32_t rc_base = et_s + (uint32_t)d * kECap * 8u;
-  uint32_t ptr[4];
-  int rem[4];
-  int maxn = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int lr = wa * 8 + 2 * i + hw;
-    int beg = 0;
-    rem[i] = 0;
-    if (lr < nrows) {
-      beg = (int)lds_u32(rp_s + (uint32_t)lr * 4u) - ebase;
-      rem[i] = (int)lds_u32(rp_s + (uint32_t)lr * 4u + 4u) - ebase - beg;
-    }
-    ptr[i] = rc_base + (uint32_t)beg * 8u;
-    maxn = max(maxn, rem[i]);
-  }
-  maxn = __reduce_max_sync(0xffffffffu, maxn);
-  float2 S[4], Q[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) S[i] = Q[i] = make_float2(0.f, 0.f);
-  if (fits) {
-    float2 v[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[i][k] = make_float2(0.f, 0.f);
-    for (; maxn > 0; maxn -= 4) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gather_slot(v[i][k], ptr[i] + 8u * k, rem[i], k, tb);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < rem[i]) {
-            const float c = lds_f32(ptr[i] + 8u * k + 4u);
-            const float2 cc = make_float2(c, c);
-            S[i] = __ffma2_rn(cc, v[i][k], S[i]);
-            Q[i] = __ffma2_rn(cc, make_float2(fabsf(v[i][k].x), fabsf(v[i][k].y)), Q[i]);
-          }
-        ptr[i] += 32u;
-        rem[i] -= 4;
-      }
-    }
-  } else {
-    // slow path (a tile whose in-edge slice overflows the staging buffer): one edge at a time, overflow from global
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int beg = (int)((ptr[i] - rc_base) >> 3);
-      for (int e = 0; e < rem[i]; ++e) {
-        const int idx = beg + e;
-        uint32_t off;
-        float c;
-        if (idx < kECap) {
-          off = lds_u32(rc_base + (uint32_t)idx * 8u);
-          c = lds_f32(rc_base + (uint32_t)idx * 8u + 4u);
-        } else {
-          const int64_t ge = (int64_t)ebase + idx;
-          const float w = dd.w ? dd.w[ge] : 1.0f;
-          c = w * (w * p.prior[dd.src[ge]]);
-          off = (uint32_t)dd.rel[ge] * (uint32_t)kPnRowBytes;
-        }
-        const float2 vv = ldg2(tb + off);
-        const float2 cc = make_float2(c, c);
-        S[i] = __ffma2_rn(cc, vv, S[i]);
-        Q[i] = __ffma2_rn(cc, make_float2(fabsf(vv.x), fabsf(vv.y)), Q[i]);
-      }
-    }
-  }
+  const char* tb = dd.pn + (g * BK + 4 * c8) * 4;
+  const uint32_t qb_s = et_s + (uint32_t)offsetof(ETile<NI>, qbase) + (uint32_t)d * (BM / 4 + 4) * 4u;
+  const uint32_t rc_s = et_s + (uint32_t)d * kECap * 8u + (uint32_t)r * 8u;
+  const uint32_t xs = et_s + (uint32_t)offsetof(ETile<NI>, x) + (uint32_t)((g * BK + 4 * c8) * 4);
   const float2 one = make_float2(1.f, 1.f), mone = make_float2(-1.f, -1.f);
-  const uint32_t xs = et_s + (uint32_t)offsetof(ETile<NI>, x) + (uint32_t)((g * BK + 2 * l16) * 4);
-  LaneX<NI> x;
-  int cur_q = -1;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int lr = wa * 8 + 2 * i + hw;
-    if (lr >= nrows) continue;
-    const int q = lr >= lr_switch ? 1 : 0;
-    if (q != cur_q) {
-      cur_q = q;
-      x.load(xs + (uint32_t)(q * NI * kXCols * 4));
+  for (int qd = 0; qd < 2; ++qd) {
+    const int quad = wa * 2 + qd;
+    const int lr = quad * 4 + r;
+    if (quad * 4 >= nrows) break;                            // warp uniform
+    Acc4 acc;
+    acc.clear();
+    if (fits) {
+      const int qb = (int)lds_u32(qb_s + (uint32_t)quad * 4u);
+      int m = ((int)lds_u32(qb_s + (uint32_t)quad * 4u + 4u) - qb) >> 2;     // slots of this quad (warp uniform)
+      uint32_t es = rc_s + (uint32_t)qb * 8u;
+      const uint32_t zs = et_s + (uint32_t)offsetof(ETile<NI>, zero_entry);
+      for (; m > 0; m -= 8, es += 8 * 32) {
+        // 8 slots per round, no predicates: slots past the quad's block read the zero entry (table row 0 x 0)
+        float4 v[8];
+        float c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint2 e = lds_u2(k < m ? es + (uint32_t)k * 32u : zs);
+          c[k] = __uint_as_float(e.y);
+          v[k] = ldg4(tb + e.x);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc.add(c[k], v[k]);
+      }
+    } else if (lr < nrows) {
+      // slow path (the tile's slot-major blocks overflow the staging buffer): every lane walks its own row in the CSR
+      const uint32_t rp_s = et_s + (uint32_t)offsetof(ETile<NI>, rowptr) + (uint32_t)d * (BM + 4) * 4u;
+      const int beg = (int)lds_u32(rp_s + (uint32_t)lr * 4u), end = (int)lds_u32(rp_s + (uint32_t)lr * 4u + 4u);
+      for (int e = beg; e < end; ++e) {
+        const float w = dd.w ? dd.w[e] : 1.0f;
+        const float c = w * (w * p.prior[dd.src[e]]);
+        acc.add(c, ldg4(tb + (uint32_t)dd.rel[e] * (uint32_t)kPnRowBytes));
+      }
     }
-    const float2 U = __ffma2_rn(S[i], one, Q[i]), V = __ffma2_rn(S[i], mone, Q[i]);
-    const uint32_t off = (uint32_t)lr * 64u + ((uint32_t)((l16 >> 2) ^ ((lr >> 1) & 3)) << 4) + (uint32_t)(l16 & 3) * 4u;
+    if (lr < nrows) {
+      const float2 U0 = __ffma2_rn(acc.s0, one, acc.q0), V0 = __ffma2_rn(acc.s0, mone, acc.q0);
+      const float2 U1 = __ffma2_rn(acc.s1, one, acc.q1), V1 = __ffma2_rn(acc.s1, mone, acc.q1);
+      const int q = lr >= lr_switch ? 1 : 0;
+      const uint32_t off = (uint32_t)lr * 64u + ((uint32_t)((c8 >> 1) ^ ((lr >> 1) & 3)) << 4) + (uint32_t)(c8 & 1) * 8u;
 #pragma unroll
-    for (int j = 0; j < NI; ++j) emit_pair(a_slots + (uint32_t)((d * NI + j) * 2 * kABytes) + off, x.xp[j], x.xn[j], U, V);
+      for (int j = 0; j < NI; ++j) {
+        const float4 x = lds_f4(xs + (uint32_t)((q * NI + j) * kXCols * 4));
+        emit_quad(a_slots + (uint32_t)((d * NI + j) * 2 * kABytes) + off, x, U0, U1, V0, V1);
+      }
+    }
   }
 }
 
@@ -421,7 +470,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
     for (int t = 0; t < T; ++t) { mbar_init(&afull[t], t == T - 1 ? 1 : kAggWarps); mbar_init(&aempty[t], 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps);
-      mbar_init(&efull[a], 32); mbar_init(&eempty[a], kAggWarps);
+      mbar_init(&efull[a], 2); mbar_init(&eempty[a], kAggWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -445,17 +494,30 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
     if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      Prof pf; pf.init(p.debug & 32);
       uint32_t wphase = 0, grp = 0;
       int ws = 0;
       const int w_rows = p.n_pad / CS;
       const int w_slice = w_rows * BK * 2;
       for (int tg = cid; tg < ngroups; tg += ncluster) {
         const int m0 = (tg * CS + crank) * BM;
+        // the h planes come from HBM: pull the NEXT tile's blocks into L2 now, so that their TMA loads (issued only
+        // ~3 k-blocks ahead of the MMA) see L2 latency
+        if (tg + ncluster < ngroups) {
+          const int m1 = ((tg + ncluster) * CS + crank) * BM;
+          for (int g = 0; g < G; ++g) {
+            tma_prefetch_2d(&map_h_hi, g * BK, m1);
+            tma_prefetch_2d(&map_h_lo, g * BK, m1);
+          }
+        }
         for (int g = 0; g < G; ++g, ++grp) {
           for (int t = 0; t < T; ++t) {
             const int kcol = (g * T + t) * BK;
-            mbar_wait_sleep(&wempty[ws], wphase ^ 1, 1);
+            { const long long t0 = pf.t(); mbar_wait_sleep(&wempty[ws], wphase ^ 1, 1); pf.add(0, t0); }
             uint8_t* st = w_ring + (size_t)ws * 2 * w_bytes;
+            if (p.debug & 8) {                                   // timing experiment: no W traffic
+              mbar_arrive(&wfull[ws]);
+            } else {
             mbar_expect_tx(&wfull[ws], (uint32_t)(2 * w_bytes));
             if (CS == 1) {
               tma_load_2d(st, &map_w_hi, &wfull[ws], kcol, 0);
@@ -464,37 +526,42 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
               tma_load_2d_mc(st + crank * w_slice, &map_w_hi, &wfull[ws], kcol, crank * w_rows, kMask);
               tma_load_2d_mc(st + w_bytes + crank * w_slice, &map_w_lo, &wfull[ws], kcol, crank * w_rows, kMask);
             }
+            }
             if (++ws == kNW) { ws = 0; wphase ^= 1; }
-            if (t == T - 1) {                                      // the h block of this group
-              mbar_wait_sleep(&aempty[t], (grp & 1) ^ 1, 2);
-              uint8_t* as = a_slots + (size_t)t * 2 * kABytes;
-              mbar_expect_tx(&afull[t], (uint32_t)(2 * kABytes));
-              tma_load_2d(as, &map_h_hi, &afull[t], g * BK, m0);
-              tma_load_2d(as + kABytes, &map_h_lo, &afull[t], g * BK, m0);
+            if (t == 0) {                                          // the h block leads its group (operand slot T-1)
+              { const long long t0 = pf.t(); mbar_wait_sleep(&aempty[T - 1], (grp & 1) ^ 1, 2); pf.add(1, t0); }
+              uint8_t* as = a_slots + (size_t)(T - 1) * 2 * kABytes;
+              mbar_expect_tx(&afull[T - 1], (uint32_t)(2 * kABytes));
+              tma_load_2d(as, &map_h_hi, &afull[T - 1], g * BK, m0);
+              tma_load_2d(as + kABytes, &map_h_lo, &afull[T - 1], g * BK, m0);
             }
           }
         }
       }
+      pf.store(5, 2);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+      Prof pf; pf.init(p.debug & 32);
+      const long long t_all = pf.t();
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       uint32_t wphase = 0, grp = 0;
       int ws = 0, it = 0;
       for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
         const int acc = it & 1;
-        mbar_wait_sleep(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 3);
+        { const long long t0 = pf.t(); mbar_wait_sleep(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 3); pf.add(3, t0); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
         for (int g = 0; g < G; ++g, ++grp) {
           const int ksteps = g == G - 1 ? p.ksteps_last : BK / UMMA_K;
           for (int t = 0; t < T; ++t) {
-            mbar_wait_sleep(&wfull[ws], wphase, 4);
-            mbar_wait_sleep(&afull[t], grp & 1, 10 + t);
+            const int sl = t == 0 ? T - 1 : t - 1;              // operand slot of block t (slot T-1 = the h block)
+            { const long long t0 = pf.t(); mbar_wait_sleep(&wfull[ws], wphase, 4); pf.add(0, t0); }
+            { const long long t0 = pf.t(); mbar_wait_sleep(&afull[sl], grp & 1, 10 + sl); pf.add(t == 0 ? 2 : 1, t0); }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_u32(a_slots + (size_t)t * 2 * kABytes);
+            const uint32_t sa = smem_u32(a_slots + (size_t)sl * 2 * kABytes);
             const uint32_t sw = smem_u32(w_ring + (size_t)ws * 2 * w_bytes);
             const uint64_t da_hi = make_smem_desc<BK>(sa), da_lo = make_smem_desc<BK>(sa + kABytes);
             const uint64_t dw_hi = make_smem_desc<BK>(sw), dw_lo = make_smem_desc<BK>(sw + w_bytes);
@@ -505,40 +572,52 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
               umma_bf16(tmem_d, da_lo + adv, dw_hi + adv, idesc, 1u);
             }
             if (CS == 1) umma_commit(&wempty[ws]); else umma_commit_mc(&wempty[ws], kMask);
-            umma_commit(&aempty[t]);
+            umma_commit(&aempty[sl]);
             if (++ws == kNW) { ws = 0; wphase ^= 1; }
           }
         }
         umma_commit(&tmem_full[acc]);
       }
+      pf.total(0, t_all);
+      pf.store(1, 4);
     }
-  } else if (warp == 3) {
-    // ===================== edge stager =====================
+  } else {
+    // ===================== edge stagers: warp 3 direction 0 (+ header, instructions), warp 2 direction 1 ==========
+    Prof pf; pf.init((p.debug & 32) && warp == 3 && lane == 0);
     int it = 0;
     for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
       const int eb = it & 1;
-      if (it >= 2) mbar_wait_sleep(&eempty[eb], ((it >> 1) - 1) & 1, 5);
-      stage_tile<NI>(etile[eb], p, tg * CS + crank, lane);
-      __syncwarp();
-      mbar_arrive(&efull[eb]);
+      long long t0 = pf.t();
+      if (it >= 2) mbar_wait_sleep(&eempty[eb], ((it >> 1) - 1) & 1, 5, 500);
+      pf.add(0, t0);
+      t0 = pf.t();
+      stage_tile<NI>(etile[eb], p, tg * CS + crank, lane, 3 - warp, &efull[eb]);
+      pf.add(1, t0);
     }
+    pf.store(11, 2);
   }
   } else if (warp >= kFirstAgg) {
     // ===================== aggregation warps =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int wa = warp - kFirstAgg;
+    Prof pf; pf.init((p.debug & 32) && wa == 0 && lane == 0);
+    const long long t_all = pf.t();
     uint32_t grp = 0;
     int it = 0;
     for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
       const int eb = it & 1;
-      mbar_wait_sleep(&efull[eb], (it >> 1) & 1, 6);
+      { const long long t0 = pf.t(); mbar_wait_sleep(&efull[eb], (it >> 1) & 1, 6, 200); pf.add(1, t0); }
       const ETile<NI>& et = etile[eb];
       for (int g = 0; g < G; ++g, ++grp) {
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
+          long long t0 = pf.t();
 #pragma unroll
-          for (int j = 0; j < NI; ++j) mbar_wait_sleep(&aempty[d * NI + j], (grp & 1) ^ 1, 20 + d * NI + j);
-          agg_pass<NI>(et, p, d, g, wa, lane, smem_u32(a_slots));
+          for (int j = 0; j < NI; ++j) mbar_wait_sleep(&aempty[d * NI + j], (grp & 1) ^ 1, 20 + d * NI + j, 100);
+          pf.add(0, t0);
+          t0 = pf.t();
+          if (!(p.debug & 1)) agg_pass<NI>(et, p, d, g, wa, lane, smem_u32(a_slots));
+          pf.add(2, t0);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
@@ -550,6 +629,8 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&eempty[eb]);
     }
+    pf.total(7, t_all);
+    pf.store(8, 3);
   } else {
     // ===================== epilogue =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -561,17 +642,19 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
     uint32_t* s_h = reinterpret_cast<uint32_t*>(s_out + BM * 16 * 4) + row_in_tile * 8;
     uint32_t* s_l = reinterpret_cast<uint32_t*>(s_out + BM * 16 * 4 + BM * 16 * 2) + row_in_tile * 8;
     const bool issuer = warp == kFirstEpi && lane == 0;
+    Prof pf; pf.init((p.debug & 32) && issuer);
+    const long long t_all = pf.t();
     int it = 0;
     for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
       const int tile = tg * CS + crank;
       const int acc = it & 1;
-      mbar_wait_sleep(&tmem_full[acc], (it >> 1) & 1, 7);
+      { const long long t0 = pf.t(); mbar_wait_sleep(&tmem_full[acc], (it >> 1) & 1, 7, 500); pf.add(0, t0); }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row = (int64_t)tile * BM + row_in_tile;
       const bool row_ok = row < p.M;
       float dot = 0.f;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
-      for (int ch = 0; ch < nchunks; ++ch) {
+      for (int ch = (p.debug & 16) ? nchunks - 1 : 0; ch < nchunks; ++ch) {     // debug 16: last chunk only
         const int c0 = ch * 16;
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c0, r);
@@ -616,7 +699,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         named_bar_sync(1, kEpiWarps * 32);
-        if (issuer) {
+        if (issuer && !(p.debug & 4)) {
           const int m0 = tile * BM;
           if (p.C) tma_store_2d(&map_c, s_out, c0, m0);
           if (p.has_planes) {
@@ -632,6 +715,8 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    pf.total(14, t_all);
+    pf.store(13, 1);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -641,6 +726,115 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccStride)
                  : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per batch: quad-ELL build.  grid = (ntiles, 2 directions), 128 threads = the rows of the tile
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BM) fused_ell_build_kernel(FDir d0, FDir d1, EllView ell, int64_t Nt) {
+  const int tile = blockIdx.x, d = blockIdx.y;
+  const FDir dd = d == 0 ? d0 : d1;
+  const int64_t r0 = (int64_t)tile * BM;
+  const int r = threadIdx.x, lane = r & 31, warp = r >> 5;
+  const int64_t row = r0 + r;
+  int beg = 0, deg = 0;
+  if (row < Nt) {
+    beg = dd.rowptr[row];
+    deg = dd.rowptr[row + 1] - beg;
+  }
+  int m = max(deg, __shfl_xor_sync(0xffffffffu, deg, 1));
+  m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));                 // slots of this row's quad
+  __shared__ int s_q[BM / 4 + 1];
+  __shared__ int s_base;
+  if ((r & 3) == 0) s_q[r >> 2] = 4 * m;
+  __syncthreads();
+  if (warp == 0) {                                                // exclusive scan over the 32 quads
+    const int v = s_q[lane];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    s_q[lane] = incl - v;
+    if (lane == 31) {
+      s_q[32] = incl;
+      int base = -1;
+      if (incl <= kECap) {                                        // larger tiles take the fused kernel's slow path
+        base = atomicAdd(ell.counters + d, incl);
+        if ((int64_t)base + incl > ell.cap) base = -1;            // arrays full (cannot happen with cap >= 4 F): slow path
+      }
+      s_base = base;
+    }
+  }
+  __syncthreads();
+  int32_t* qr = ell.qrow + ((int64_t)d * ell.ntiles + tile) * kQRow;
+  if (r <= 32) qr[r] = s_q[r];
+  if (r == 33) qr[33] = s_base;
+  if (r > 33 && r < kQRow) qr[r] = 0;
+  const int base = s_base;
+  if (base < 0) return;
+  const int64_t o = (int64_t)d * ell.cap + base + s_q[r >> 2] + (r & 3);
+  for (int k = 0; k < m; ++k) {
+    int sn = 0;
+    uint32_t off = 0;
+    float w = 0.f;
+    if (k < deg) {
+      sn = dd.src[beg + k];
+      off = (uint32_t)dd.rel[beg + k] * (uint32_t)kPnRowBytes;
+      w = dd.w ? dd.w[beg + k] : 1.0f;
+    }
+    ell.src[o + 4 * k] = sn;
+    ell.off[o + 4 * k] = off;
+    ell.w[o + 4 * k] = w;
+  }
+}
+
+// per layer: rc[e] = {off[e], w (w prior[src[e]])} for the allocated entries of both directions (reasongnn.py:80-84)
+__global__ void fused_coef_kernel(EllView ell, const float* __restrict__ prior) {
+  const int d = blockIdx.y;
+  const int n = min((int64_t)ell.counters[d], ell.cap);
+  const int64_t o = (int64_t)d * ell.cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float w = ell.w[o + i];
+    ell.rc[o + i] = make_int2((int)ell.off[o + i], __float_as_int(w * (w * __ldg(prior + ell.src[o + i]))));
+  }
+}
+
+struct EllPlan {
+  int64_t cap;
+  int ntiles;
+  size_t o_qrow, o_src, o_off, o_w, o_rc, bytes;
+};
+
+EllPlan plan_ell(int64_t Nt, int64_t F) {
+  EllPlan e{};
+  e.ntiles = (int)ceil_div(Nt, BM);
+  // sum over quads of 4 * max degree <= 4 F; typical graphs need ~1.6 F.  2 F + 4 Nt covers them, tiles that do not
+  // fit any more fall back to the slow path of the fused kernel
+  e.cap = (int64_t)align_up((size_t)(2 * F + 4 * Nt + 64), 64);
+  size_t o = 256;
+  e.o_qrow = o; o += align_up((size_t)2 * e.ntiles * kQRow * 4, 256);
+  e.o_src = o;  o += align_up((size_t)2 * e.cap * 4, 256);
+  e.o_off = o;  o += align_up((size_t)2 * e.cap * 4, 256);
+  e.o_w = o;    o += align_up((size_t)2 * e.cap * 4, 256);
+  e.o_rc = o;   o += align_up((size_t)2 * e.cap * 8, 256);
+  e.bytes = o;
+  return e;
+}
+
+EllView ell_view(void* blob, const EllPlan& e) {
+  char* b = reinterpret_cast<char*>(blob);
+  EllView v{};
+  v.counters = reinterpret_cast<int32_t*>(b);
+  v.qrow = reinterpret_cast<int32_t*>(b + e.o_qrow);
+  v.src = reinterpret_cast<int32_t*>(b + e.o_src);
+  v.off = reinterpret_cast<uint32_t*>(b + e.o_off);
+  v.w = reinterpret_cast<float*>(b + e.o_w);
+  v.rc = reinterpret_cast<int2*>(b + e.o_rc);
+  v.cap = e.cap;
+  v.ntiles = e.ntiles;
+  return v;
 }
 
 struct FusedPlan {
@@ -705,6 +899,13 @@ int launch_fused(const CUtensorMap& m_h_hi, const CUtensorMap& m_h_lo, const CUt
 }  // namespace
 }  // namespace gr
 
+extern "C" int gr_fused_profile_read(unsigned long long* out, int n) {
+  using namespace gr;
+  GR_CHECK_ARG(out && n > 0 && n <= 160 * 16, "bad buffer");
+  GR_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_fused_prof, sizeof(unsigned long long) * (size_t)n));
+  return GR_OK;
+}
+
 extern "C" int gr_fused_layer_supported(int64_t N_nodes, int64_t D, int64_t seg_pitch, int I, int64_t N_out) {
   return gr::plan_fused(N_nodes, D, seg_pitch, I, N_out).ok ? 1 : 0;
 }
@@ -714,6 +915,33 @@ extern "C" size_t gr_fused_layer_workspace_bytes(int64_t D, int64_t seg_pitch, i
   return 2 * gr::plan_fused(gr::tc::BM, D, seg_pitch, I, N_out).w_plane_bytes;
 }
 
+extern "C" size_t gr_fused_ell_bytes(int B, int N_nodes, int64_t F) {
+  if (B <= 0 || N_nodes <= 0 || F < 0) return 0;
+  return gr::plan_ell((int64_t)B * N_nodes, F).bytes;
+}
+
+extern "C" int gr_fused_ell_build(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
+                                  const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
+                                  int B, int N_nodes, int64_t F, void* ell, size_t ell_bytes, void* stream_) {
+  using namespace gr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  GR_CHECK_ARG(rowptr_t && rowptr_h && ell, "null pointer");
+  GR_CHECK_ARG(F == 0 || (src_t && rel_t && src_h && rel_h), "null edge arrays");
+  GR_CHECK_ARG(B > 0 && N_nodes > 0, "sizes must be positive");
+  const int64_t Nt = (int64_t)B * N_nodes;
+  const EllPlan e = plan_ell(Nt, F);
+  if (ell_bytes < e.bytes || (reinterpret_cast<uintptr_t>(ell) & 255) != 0) {
+    set_error("gr_fused_ell_build: buffer too small (%zu < %zu) or not 256-byte aligned", ell_bytes, e.bytes);
+    return GR_ERR_WORKSPACE;
+  }
+  EllView v = ell_view(ell, e);
+  GR_CHECK_CUDA(cudaMemsetAsync(v.counters, 0, 256, stream));
+  FDir d0{rowptr_t, src_t, rel_t, w_t, nullptr}, d1{rowptr_h, src_h, rel_h, w_h, nullptr};
+  fused_ell_build_kernel<<<dim3((unsigned)e.ntiles, 2), BM, 0, stream>>>(d0, d1, v, Nt);
+  GR_CHECK_LAUNCH();
+  return GR_OK;
+}
+
 extern "C" int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
                               const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
                               const float* prior, const float* pn_fwd, const float* pn_inv, const float* ins,
@@ -721,10 +949,10 @@ extern "C" int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, con
                               int64_t ldw, const float* bias, float* C, int64_t ldc, void* C_hi, void* C_lo,
                               int64_t ldc16, const float* w_score, float* dots, int B, int N_nodes, int D, int I,
                               int64_t N_out, int64_t F, uint32_t flags, void* workspace, size_t workspace_bytes,
-                              void* stream_) {
+                              void* ell, size_t ell_bytes, void* stream_) {
   using namespace gr;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  GR_CHECK_ARG(rowptr_t && rowptr_h && prior && pn_fwd && pn_inv && ins && h_hi && h_lo && W && workspace,
+  GR_CHECK_ARG(rowptr_t && rowptr_h && prior && pn_fwd && pn_inv && ins && h_hi && h_lo && W && workspace && ell,
                "null pointer");
   GR_CHECK_ARG(F == 0 || (src_t && rel_t && src_h && rel_h), "null edge arrays");
   GR_CHECK_ARG(C || C_hi, "no output requested");
@@ -747,6 +975,11 @@ extern "C" int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, con
     set_error("gr_fused_layer: workspace too small or not 256-byte aligned");
     return GR_ERR_WORKSPACE;
   }
+  const EllPlan ep = plan_ell(M, F);
+  if (ell_bytes < ep.bytes || (reinterpret_cast<uintptr_t>(ell) & 255) != 0) {
+    set_error("gr_fused_layer: quad-ELL buffer too small or not 256-byte aligned (gr_fused_ell_bytes / gr_fused_ell_build)");
+    return GR_ERR_WORKSPACE;
+  }
   char* ws = reinterpret_cast<char*>(workspace);
   __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(ws + f.w_plane_bytes);
@@ -759,11 +992,16 @@ extern "C" int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, con
   FParams p{};
   p.dir[0] = FDir{rowptr_t, src_t, rel_t, w_t, reinterpret_cast<const char*>(pn_fwd)};
   p.dir[1] = FDir{rowptr_h, src_h, rel_h, w_h, reinterpret_cast<const char*>(pn_inv)};
+  p.ell = ell_view(ell, ep);
+  // per layer: the entries' coefficients c_f = w (w prior[src]) next to their table offsets, one streaming pass
+  fused_coef_kernel<<<dim3((unsigned)(2 * sm_count()), 2), 256, 0, stream>>>(p.ell, prior);
+  GR_CHECK_LAUNCH();
   p.prior = prior; p.ins = ins; p.bias = bias; p.C = C; p.ldc = ldc; p.w_score = w_score; p.dots = dots;
   p.M = (int)M; p.N = (int)N_out; p.n_pad = f.n_pad; p.D = D; p.B = B; p.Nq = N_nodes; p.G = f.G;
   p.ksteps_last = f.ksteps_last; p.num_tiles = (int)ceil_div(M, BM);
   p.has_planes = C_hi ? 1 : 0;
   p.flags = flags;
+  p.debug = g_fused_debug;
   const int cs = ((f.n_pad / 2) % 8 == 0 && p.num_tiles >= 2) ? 2 : 1;
   CUtensorMap m_h_hi, m_h_lo, m_w_hi, m_w_lo, m_c, m_c_hi, m_c_lo;
   // the h planes are exposed with seg_pitch columns only: the box of the last column group is zero filled beyond them

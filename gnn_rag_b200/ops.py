@@ -348,6 +348,24 @@ def fused_layer_supported(N, D, seg_pitch, I, n_out):
     return bool(_L().gr_fused_layer_supported(N, D, seg_pitch, I, n_out))
 
 
+def fused_ell(g, w_t=None, w_h=None):
+    """Quad-ELL form of the batch's CSRs for the fused layer kernel, built once per batch and cached on the graph
+    (keyed on whether edge weights are used: they are part of the static entries)."""
+    key = "_ell_w" if w_t is not None else "_ell"
+    ell = getattr(g, key, None)
+    if ell is None:
+        L = _L()
+        nbytes = L.gr_fused_ell_bytes(g.B, g.N, g.F)
+        ell = torch.empty(nbytes, dtype=torch.uint8, device=g.rowptr_t.device)
+        with _OpTimer("csr_build"):
+            _lib.check(L.gr_fused_ell_build(_p(g.rowptr_t), _p(g.src_t), _p(g.rel_t), _p(w_t),
+                                            _p(g.rowptr_h), _p(g.src_h), _p(g.rel_h), _p(w_h),
+                                            g.B, g.N, g.F, _p(ell), nbytes, _stream()))
+        STATS.launches += 1
+        setattr(g, key, ell)
+    return ell
+
+
 def fused_layer(g, prior, pn_fwd, pn_inv, ins, h_planes, seg_pitch, W, bias, out=None, out_planes=None,
                 w_score=None, dots=None, relu=True, w_t=None, w_h=None):
     """One dense-prior ReaRev layer in one kernel (reasongnn.py:134-165): both directions and all instructions are
@@ -363,6 +381,7 @@ def fused_layer(g, prior, pn_fwd, pn_inv, ins, h_planes, seg_pitch, W, bias, out
     L = _L()
     nbytes = L.gr_fused_layer_workspace_bytes(D, seg_pitch, I, n_out)
     ws, presplit = _weight_ws(W, n_out, W.shape[1], "fused", seg_pitch, nbytes)
+    ell = fused_ell(g, w_t, w_h)
     chi, clo = out_planes if out_planes is not None else (None, None)
     flags = (LINEAR_RELU if relu else 0) | (LINEAR_W_PRESPLIT if presplit else 0)
     with _OpTimer("fused_layer"):
@@ -371,9 +390,9 @@ def fused_layer(g, prior, pn_fwd, pn_inv, ins, h_planes, seg_pitch, W, bias, out
                               _p(prior), _p(pn_fwd), _p(pn_inv), _p(ins), _p(hi), _p(lo), hi.stride(0), seg_pitch,
                               _p(W), W.stride(0), _p(bias), _p(out), out.stride(0) if out is not None else 0,
                               _p(chi), _p(clo), chi.stride(0) if chi is not None else 0, _p(w_score), _p(dots),
-                              B, g.N, D, I, n_out, g.F, flags, _p(ws), ws.numel(), _stream())
+                              B, g.N, D, I, n_out, g.F, flags, _p(ws), ws.numel(), _p(ell), ell.numel(), _stream())
     _lib.check(rc)
-    STATS.launches += 1
+    STATS.launches += 2
     return out
 
 

@@ -219,8 +219,18 @@ int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src_t, const i
  * Supported (gr_fused_layer_supported): I <= 2, N >= 128, seg_pitch % 16 == 0, seg_pitch <= 256, N_out <= 256 and the
  * operand stages must fit shared memory (D = N_out = 200 does).  The A operand is bit-identical to the unfused pair;
  * the tensor core accumulates the k-blocks in a different order (fp32 rounding). */
+/* Diagnostic: per-CTA wait-cycle counters of the last gr_fused_layer launch made with gr_set_option("fused_debug", 32)
+ * (16 uint64 per CTA, slot meaning in csrc/fused_layer.cu). */
+int gr_fused_profile_read(unsigned long long* out, int n);
 int gr_fused_layer_supported(int64_t N_nodes, int64_t D, int64_t seg_pitch, int I, int64_t N_out);
 size_t gr_fused_layer_workspace_bytes(int64_t D, int64_t seg_pitch, int I, int64_t N_out);
+/* Once per batch: both CSRs of gr_csr_build re-laid out slot-major per quad of 4 rows ("quad ELL", csrc/fused_layer.cu)
+ * into `ell` (gr_fused_ell_bytes, 256-byte aligned); gr_fused_layer reads it and keeps its per-layer {table offset,
+ * coefficient} scratch inside the same buffer. */
+size_t gr_fused_ell_bytes(int B, int N_nodes, int64_t F);
+int gr_fused_ell_build(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
+                       const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
+                       int B, int N_nodes, int64_t F, void* ell, size_t ell_bytes, void* stream);
 int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rel_t, const float* w_t,
                    const int32_t* rowptr_h, const int32_t* src_h, const int32_t* rel_h, const float* w_h,
                    const float* prior, const float* pn_fwd, const float* pn_inv, const float* ins,
@@ -228,7 +238,7 @@ int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, const int32_t*
                    int64_t ldw, const float* bias, float* C, int64_t ldc, void* C_hi, void* C_lo,
                    int64_t ldc16, const float* w_score, float* dots, int B, int N_nodes, int D, int I,
                    int64_t N_out, int64_t F, uint32_t flags, void* workspace, size_t workspace_bytes,
-                   void* stream);
+                   void* ell, size_t ell_bytes, void* stream);
 
 /* Diagnostic only (scripts/agg_probe.py): replays the aggregation kernel's store pattern without any edge work. */
 int gr_debug_store_probe(void* hi, void* lo, int64_t Nt, int64_t ld, int col_start, int ncols, int mode,
