@@ -58,7 +58,7 @@ constexpr int kFirstEpi = 4, kFirstAgg = 8;
 constexpr int kThreads = (kFirstAgg + kAggWarps) * 32;      // 768
 constexpr int kNW = 3;                       // W ring stages
 constexpr int kECap = 1024;                  // staged in-edges per direction per tile (mean 512 at cfg2); rest: slow path
-constexpr int kXCols = 256;                  // instruction columns kept per question (zero padded)
+constexpr int kXCols = 224;                  // instruction columns kept per question: 7 groups of 32 (zero padded)
 constexpr int kPnRowBytes = 1024;            // padded relation table: 256 fp32 per row (gr_pad_table256)
 constexpr int kABytes = BM * BK * 2;         // one bf16 plane of an A slot: 8 KB
 constexpr int kOutBytes = BM * 16 * 4 + 2 * BM * 16 * 2;    // epilogue staging: fp32 8 KB + hi 4 KB + lo 4 KB
@@ -114,7 +114,7 @@ struct FParams {
 template <int NI>
 struct alignas(16) ETile {
   int2 rc[2][kECap];
-  float x[2][NI][kXCols];             // raw instruction vectors of the tile's two questions
+  float x[2][NI][2][kXCols];          // relu(+x)/2 | relu(-x)/2 of the instruction vectors of the tile's two questions
   int32_t rowptr[2][BM + 4];          // global edge indices (slow path, and the stager's own row lookup)
   int32_t qbase[2][kQRow];            // entry offset of each quad's block, [BM/4] = total entries (bulk copy of the ELL row)
   int32_t nrows, lr_switch, fits[2];
@@ -286,7 +286,9 @@ __device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int 
       for (int i = lane; i < 2 * NI * kXCols; i += 32) {
         const int c = i % kXCols, j = (i / kXCols) % NI, q = i / (kXCols * NI);
         const int b = b0 + q;
-        (&et.x[0][0][0])[i] = (c < p.D && b < p.B) ? __ldg(p.ins + ((int64_t)b * NI + j) * p.D + c) : 0.f;
+        const float v = (c < p.D && b < p.B) ? __ldg(p.ins + ((int64_t)b * NI + j) * p.D + c) : 0.f;
+        et.x[q][j][0][c] = 0.5f * fmaxf(v, 0.f);
+        et.x[q][j][1][c] = 0.5f * fmaxf(-v, 0.f);
       }
     }
     if (!fits) {
@@ -313,6 +315,8 @@ __device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int 
 // ---------------------------------------------------------------------------------------------------------
 // aggregation: one pass = (direction d, column group g) for this warp's 8 rows (2 quads) -> I A-operand blocks
 // ---------------------------------------------------------------------------------------------------------
+// (ld.global.nc.L1::no_allocate for this gather was measured: 489 us instead of 270 -- even the ~28 KB of L1 left next to
+// 226 KB of shared memory serve enough of the quads' repeated table lines to matter)
 __device__ __forceinline__ float4 ldg4(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 lds_f4(uint32_t a) {
   float4 v;
@@ -342,12 +346,10 @@ struct Acc4 {                                   // S = sum c*v, Q = sum c*|v| fo
 
 // y = xp * (Q + S) + xn * (Q - S) for 4 columns (xp = relu(x)/2, xn = relu(-x)/2), split into bf16 hi / lo, 8-byte
 // stores into the K-major SWIZZLE_64B operand tile
-__device__ __forceinline__ void emit_quad(uint32_t slot, const float4& x, const float2& U0, const float2& U1,
-                                          const float2& V0, const float2& V1) {
-  const float2 xp0 = make_float2(0.5f * fmaxf(x.x, 0.f), 0.5f * fmaxf(x.y, 0.f));
-  const float2 xp1 = make_float2(0.5f * fmaxf(x.z, 0.f), 0.5f * fmaxf(x.w, 0.f));
-  const float2 xn0 = make_float2(0.5f * fmaxf(-x.x, 0.f), 0.5f * fmaxf(-x.y, 0.f));
-  const float2 xn1 = make_float2(0.5f * fmaxf(-x.z, 0.f), 0.5f * fmaxf(-x.w, 0.f));
+__device__ __forceinline__ void emit_quad(uint32_t slot, const float4& xp, const float4& xn, const float2& U0,
+                                          const float2& U1, const float2& V0, const float2& V1) {
+  const float2 xp0 = make_float2(xp.x, xp.y), xp1 = make_float2(xp.z, xp.w);
+  const float2 xn0 = make_float2(xn.x, xn.y), xn1 = make_float2(xn.z, xn.w);
   float2 y0 = __fmul2_rn(xp0, U0), y1 = __fmul2_rn(xp1, U1);
   y0 = __ffma2_rn(xn0, V0, y0);
   y1 = __ffma2_rn(xn1, V1, y1);
@@ -418,8 +420,9 @@ __device__ __forceinline__ void agg_pass(const ETile<NI>& et, const FParams& p, 
       const uint32_t off = (uint32_t)lr * 64u + ((uint32_t)((c8 >> 1) ^ ((lr >> 1) & 3)) << 4) + (uint32_t)(c8 & 1) * 8u;
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
-        const float4 x = lds_f4(xs + (uint32_t)((q * NI + j) * kXCols * 4));
-        emit_quad(a_slots + (uint32_t)((d * NI + j) * 2 * kABytes) + off, x, U0, U1, V0, V1);
+        const float4 xp = lds_f4(xs + (uint32_t)(((q * NI + j) * 2) * kXCols * 4));
+        const float4 xn = lds_f4(xs + (uint32_t)(((q * NI + j) * 2 + 1) * kXCols * 4));
+        emit_quad(a_slots + (uint32_t)((d * NI + j) * 2 * kABytes) + off, xp, xn, U0, U1, V0, V1);
       }
     }
   }
@@ -852,7 +855,7 @@ FusedPlan plan_fused(int64_t Nq, int64_t D, int64_t pitch, int I, int64_t N_out)
   f.kp = (int64_t)f.G * (2 * I + 1) * BK;
   f.w_plane_bytes = align_up((size_t)N_out * f.kp * 2, 256);
   f.smem_bytes = I == 2 ? fused_smem_bytes<2>(f.n_pad) : fused_smem_bytes<1>(f.n_pad);
-  f.ok = (I == 1 || I == 2) && Nq >= BM && D >= 8 && D <= pitch && pitch % 16 == 0 && pitch <= kXCols &&
+  f.ok = (I == 1 || I == 2) && Nq >= BM && D >= 8 && D <= pitch && pitch % 16 == 0 && (pitch + BK - 1) / BK * BK <= kXCols &&
          N_out >= 8 && N_out <= 256 && f.smem_bytes <= 227 * 1024 && get_encode_fn() != nullptr;
   return f;
 }

@@ -216,7 +216,7 @@ int gr_aggregate_dual_abs(const int32_t* rowptr_t, const int32_t* src_t, const i
  *                  GR_LINEAR_W_PRESPLIT (workspace kept from an earlier call with the same W)
  *   outputs        any of C (fp32 [B*N, N_out]), C_hi / C_lo (bf16 planes, row stride ldc16), dots [2*B*N]
  *                  (dots[m] = <out[m], w_score>, dots[B*N + m] = 0: the layout gr_masked_softmax takes)
- * Supported (gr_fused_layer_supported): I <= 2, N >= 128, seg_pitch % 16 == 0, seg_pitch <= 256, N_out <= 256 and the
+ * Supported (gr_fused_layer_supported): I <= 2, N >= 128, seg_pitch % 16 == 0, seg_pitch <= 224, N_out <= 256 and the
  * operand stages must fit shared memory (D = N_out = 200 does).  The A operand is bit-identical to the unfused pair;
  * the tensor core accumulates the k-blocks in a different order (fp32 rounding). */
 /* Diagnostic: per-CTA wait-cycle counters of the last gr_fused_layer launch made with gr_set_option("fused_debug", 32)
