@@ -422,7 +422,7 @@ class ReasonGNNLayer(_GraphLayerBase):
         wt, wh = (g.w_t, g.w_h) if self.normalized_gnn else (None, None)
         e2e = getattr(self, "e2e_linear" + str(step))
         if (self.use_planes and pn is not None and ops.AGG_ABS and ops.FUSED_LAYER and not ops.ACT_BF16
-                and ops.fused_layer_supported(self.N, D, self.Dp, self.num_ins, D)):
+                and self.B * self.N >= ops.FUSED_MIN_ROWS and ops.fused_layer_supported(self.N, D, self.Dp, self.num_ins, D)):
             # aggregation produced straight into the GEMM's operand stages: the neighbour segments never reach HBM
             sw, sb = self.score_func.weight.view(-1), self.score_func.bias
             ops.fused_layer(g, current_dist, pn[0], pn[1], relational_ins, self.cur_planes(), self.Dp, e2e.weight,

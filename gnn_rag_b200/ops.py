@@ -342,6 +342,8 @@ def aggregate_dual_abs(g, prior, pn_fwd, pn_inv, ins, planes, out_col0, seg_pitc
 
 
 FUSED_LAYER = True      # dense-prior ReaRev layers: aggregation fused into the e2e GEMM (csrc/fused_layer.cu)
+FUSED_MIN_ROWS = 148 * 128   # below one 128-row tile per SM the fused kernel's serial per-tile chain (35 dependent k-blocks)
+                             # loses to the two wide kernels (cfg1: 0.853 vs 0.836 ms per step)
 
 
 def fused_layer_supported(N, D, seg_pitch, I, n_out):
