@@ -317,6 +317,8 @@ __device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int 
 // ---------------------------------------------------------------------------------------------------------
 // (ld.global.nc.L1::no_allocate for this gather was measured: 489 us instead of 270 -- even the ~28 KB of L1 left next to
 // 226 KB of shared memory serve enough of the quads' repeated table lines to matter)
+// (also measured: an L2 evict_last policy on this gather (createpolicy + ld.global.nc.L2::cache_hint) to keep the 12.5 MB
+// of relation tables resident against the 212 MB of h planes streaming through L2 -- 276 us instead of 270, no gain)
 __device__ __forceinline__ float4 ldg4(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 lds_f4(uint32_t a) {
   float4 v;
