@@ -17,18 +17,34 @@
 // sequence, same hi/lo split), so the A operand is bit-identical to the unfused path; only the order in which the
 // tensor core accumulates k-blocks differs (fp32 rounding, ~1e-7).
 //
+// Edge data: once per batch both CSRs are re-laid out slot-major per quad of 4 rows ("quad ELL",
+// fused_ell_build_kernel), once per layer one streaming pass writes {table offset, c_f} per entry (fused_coef_kernel);
+// the kernel's stagers then move a tile's entries into shared memory with ONE bulk copy per direction.  (Staging the
+// CSR slices inside the kernel -- row pointers, src / rel gathers, prior gather, a search for each edge's row -- kept
+// one warp busy for 34 us per tile and bounded the kernel at 400 us; profiles/README.md has the sequence.)
+//
 // Warp roles (768 threads, one CTA per SM, clusters of 2 share W by TMA multicast):
-//   warp 0      TMA producer: W k-blocks into a 3-stage ring, the H block of every group into its A slot
+//   warp 0      TMA producer: W k-blocks into a 3-stage ring, the H block of every group into its operand slot (the
+//               next tile's h blocks are L2-prefetched a tile ahead)
 //   warp 1      MMA issuer (one thread): tcgen05.mma cta_group::1 kind::f16, 3 products per k-step
-//   warp 2      TMEM allocator (2 x 256 columns: epilogue of tile i overlaps the mainloop of tile i+1)
-//   warp 3      edge stager: row pointers, {table byte offset, c_f} per in-edge of both CSRs, the instructions of the
-//               tile's <= 2 questions -> double-buffered shared-memory tile descriptor
+//   warps 2, 3  stagers (warp 2 also allocates TMEM: 2 x 256 columns, the epilogue of tile i overlaps the mainloop of
+//               tile i+1): bulk copies of the tile's ELL entries + quad offsets, relu(+-ins)/2 of its <= 2 questions
+//               -> double-buffered tile descriptor
 //   warps 4-7   epilogue: tcgen05.ld -> bias + relu + score dot -> fp32 h / bf16 planes via TMA stores
-//   warps 8-23  aggregation: warp a owns tile rows 8a .. 8a+7; a half-warp owns a row at a time, lane = 2 columns of
-//               the 32-column group (one 128-byte line of the padded relation table per gathered edge); 4 row pairs x 4
-//               edges = 16 independent 8-byte loads in flight per lane
-// A slots are dedicated: slot t < 2I is always written by the aggregation warps, slot 2I always by TMA, so every slot
-// barrier flips once per group and the parity is the group counter.
+//   warps 8-23  aggregation: warp a owns tile rows 8a .. 8a+7 = two quads; a quarter-warp owns a row, lane = 4 columns of
+//               the 32-column group, so one warp-wide 16-byte load gathers one in-edge of each row of the quad (one
+//               128-byte table line per row); 8 such loads in flight per lane, no predicates (slots past a quad's
+//               block read a {0, 0} entry)
+// Registers: 768 x 80 at launch; setmaxnreg hands the control (56) and epilogue (72) warp groups' surplus to the four
+// aggregation warp groups (88).  Operand slots are dedicated: slot t < 2I is always written by the aggregation warps,
+// slot 2I always by TMA, so every slot barrier flips once per group and the parity is the group counter.
+//
+// Measured (B200, cfg2: 128 000 rows, D = 200, I = 2): 270 us per layer incl. the 11 us coefficient pass, against 287 us
+// for the unfused pair (125 + 161).  Not faster than that because all three per-SM resources are near their limit at once:
+// tensor pipe 115 us of issue (3 products), the L1 / shared-memory SRAM (UMMA operand reads 2.0 MB + TMA writes 1.0 MB
+// + operand stores 0.45 MB + gathers 0.8 MB per tile; l1tex data pipe 68 %, MMA issue slows from 115 to 230 us when the
+// aggregation warps run), and the aggregation's L2 gather latency with only ~28 KB of L1 left beside 226 KB of shared
+// memory.  DESIGN.md 4.7 has the decomposition.
 #include <algorithm>
 #include <cstddef>
 
@@ -220,29 +236,12 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
                "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ float2 ldg2(const char* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 // explicit shared-state-space accesses (the carve-up of the dynamic buffer goes through integer alignment, after
 // which the compiler would fall back to generic loads / stores)
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
-}
-__device__ __forceinline__ float lds_f32(uint32_t a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float2 lds_f2(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
