@@ -397,7 +397,7 @@ def test_lstm_cluster_kernel_vs_cudnn(B, Q, D, W):
     assert max_err(got[:, -1], hn[0]) < 3e-5
 
 
-@pytest.mark.parametrize("B,N,D,I", [(4, 700, 200, 2), (3, 1500, 50, 3)])
+@pytest.mark.parametrize("B,N,D,I", [(4, 700, 200, 2), (3, 1500, 50, 3), (19, 700, 200, 2), (64, 700, 50, 3)])
 def test_query_reform_kernel_vs_torch_modules(B, N, D, I):
     from gnn_rag_b200.modules import QueryReform
     torch.manual_seed(12)
