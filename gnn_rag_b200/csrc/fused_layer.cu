@@ -91,17 +91,18 @@ struct FDir {
 // Slot-major "quad ELL" form of both CSRs, built ONCE per batch (fused_ell_build_kernel): for every 128-row tile and
 // direction a block of entries, quad Q (4 consecutive rows) owning m_Q = max in-degree of its rows slots, slot k of row r
 // at block offset qoff[Q] + 4k + r.  Static per batch: source node, relation table byte offset and edge weight of every
-// entry (padding entries: node 0, offset 0, weight 0).  Per layer one streaming pass (fused_coef_kernel) turns them into
-// {offset, c_f = w (w prior[src])} pairs, which the fused kernel's stager moves into shared memory with one bulk copy
-// per tile and direction -- no per-layer index arithmetic, no dependent gathers inside the fused kernel.
+// entry (padding entries: node -1, offset 0, weight 0).  The fused kernel's stagers move a tile's entries into shared
+// memory with one bulk copy per direction and replace the node by c_f = prior[node] there (26 independent L2 gathers per
+// lane and tile); graphs with edge weights (c_f = w (w prior[src]), normalized_gnn) take one streaming pass per layer
+// instead (fused_coef_kernel) -- no per-layer index arithmetic inside the fused kernel either way.
 constexpr int kQRow = BM / 4 + 4;     // per (direction, tile): 32 quad offsets, [32] = entries of the tile, [33] = block base
 struct EllView {
   int32_t* counters;                  // [2] entries allocated per direction (atomic bump allocator of the build)
   int32_t* qrow;                      // [2][ntiles][kQRow]
-  int32_t* src;                       // [2][cap]
-  uint32_t* off;                      // [2][cap]
-  float* w;                           // [2][cap]
-  int2* rc;                           // [2][cap] per-layer {off, c}
+  int2* ent;                          // [2][cap] static {table byte offset, source node | -1 for a padding entry}
+  float* w;                           // [2][cap] edge weights (graphs with normalized_gnn weights only)
+  int2* rc;                           // [2][cap] per-layer {off, c} (weighted graphs: fused_coef_kernel)
+  int weighted;                       // 0: c_f = prior[src], computed by the kernel's stagers from `ent`
   int64_t cap;
   int ntiles;
 };
@@ -257,7 +258,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // quad offsets and the tile's {offset, c} entries are bulk-copied from the per-layer ELL arrays; completion is counted
 // on the descriptor's full barrier (expect_tx), on which lane 0 arrives once for the warp.
 template <int NI>
-__device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int tile, int lane, int d, uint64_t* full) {
+__device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int tile, int lane, int d, uint64_t* full,
+                                           uint64_t* own, uint32_t& own_uses) {
   const int64_t r0 = (int64_t)tile * BM;
   const int nrows = tile < p.num_tiles ? (int)min((int64_t)BM, (int64_t)p.M - r0) : 0;
   int total = 0, base = 0;
@@ -301,7 +303,35 @@ __device__ __forceinline__ void stage_tile(ETile<NI>& et, const FParams& p, int 
     }
   }
   __syncwarp();                                                  // the lanes' descriptor stores precede lane 0's arrival
-  if (lane == 0 && nrows > 0 && fits) {
+  if (nrows > 0 && fits && !p.ell.weighted) {
+    // unweighted graph: copy the static {offset, node} entries to this warp's own barrier, then c_f = prior[node] in place
+    if (lane == 0) {
+      const int32_t* qr = p.ell.qrow + ((int64_t)d * p.ell.ntiles + tile) * kQRow;
+      mbar_expect_tx(own, (uint32_t)(kQRow * 4) + (uint32_t)total * 8u);
+      bulk_g2s(smem_u32(&et.qbase[d][0]), qr, (uint32_t)(kQRow * 4), own);
+      if (total > 0) bulk_g2s(smem_u32(&et.rc[d][0]), p.ell.ent + (int64_t)d * p.ell.cap + base, (uint32_t)total * 8u, own);
+    }
+    mbar_wait_sleep(own, own_uses & 1, 8, 100);
+    ++own_uses;
+    const uint32_t rc_s = smem_u32(&et.rc[d][0]) + 4u;           // the node / coefficient word of entry 0
+    for (int i0 = 0; i0 < total; i0 += 256) {
+      int node[8];
+      float c[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + lane + 32 * u;
+        node[u] = i < total ? (int)lds_u32(rc_s + (uint32_t)i * 8u) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) c[u] = node[u] >= 0 ? __ldg(p.prior + node[u]) : 0.f;   // w = 1: c_f = 1 * (1 * prior)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + lane + 32 * u;
+        if (i < total) asm volatile("st.shared.f32 [%0], %1;" ::"r"(rc_s + (uint32_t)i * 8u), "f"(c[u]) : "memory");
+      }
+    }
+    __syncwarp();
+  } else if (lane == 0 && nrows > 0 && fits) {
     const int32_t* qr = p.ell.qrow + ((int64_t)d * p.ell.ntiles + tile) * kQRow;
     tx = (uint32_t)(kQRow * 4) + (uint32_t)total * 8u;
     mbar_expect_tx(full, tx);
@@ -455,6 +485,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint64_t* efull = tmem_empty + 2;       // [2]
   uint64_t* eempty = efull + 2;           // [2]
+  uint64_t* sbar = eempty + 2;            // [2] one per stager warp: its own bulk copies
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 64);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);        // [256]
   float* s_ws = s_bias + 256;                                     // [256]
@@ -474,7 +505,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
     for (int t = 0; t < T; ++t) { mbar_init(&afull[t], t == T - 1 ? 1 : kAggWarps); mbar_init(&aempty[t], 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps);
-      mbar_init(&efull[a], 2); mbar_init(&eempty[a], kAggWarps);
+      mbar_init(&efull[a], 2); mbar_init(&eempty[a], kAggWarps); mbar_init(&sbar[a], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -588,6 +619,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
   } else {
     // ===================== edge stagers: warp 3 direction 0 (+ header, instructions), warp 2 direction 1 ==========
     Prof pf; pf.init((p.debug & 32) && warp == 3 && lane == 0);
+    uint32_t own_uses = 0;
     int it = 0;
     for (int tg = cid; tg < ngroups; tg += ncluster, ++it) {
       const int eb = it & 1;
@@ -595,7 +627,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
       if (it >= 2) mbar_wait_sleep(&eempty[eb], ((it >> 1) - 1) & 1, 5, 500);
       pf.add(0, t0);
       t0 = pf.t();
-      stage_tile<NI>(etile[eb], p, tg * CS + crank, lane, 3 - warp, &efull[eb]);
+      stage_tile<NI>(etile[eb], p, tg * CS + crank, lane, 3 - warp, &efull[eb], &sbar[3 - warp], own_uses);
       pf.add(1, t0);
     }
     pf.store(11, 2);
@@ -788,9 +820,8 @@ __global__ void __launch_bounds__(BM) fused_ell_build_kernel(FDir d0, FDir d1, E
       off = (uint32_t)dd.rel[beg + k] * (uint32_t)kPnRowBytes;
       w = dd.w ? dd.w[beg + k] : 1.0f;
     }
-    ell.src[o + 4 * k] = sn;
-    ell.off[o + 4 * k] = off;
-    ell.w[o + 4 * k] = w;
+    ell.ent[o + 4 * k] = make_int2((int)off, k < deg ? sn : -1);
+    if (ell.weighted) ell.w[o + 4 * k] = w;
   }
 }
 
@@ -801,14 +832,15 @@ __global__ void fused_coef_kernel(EllView ell, const float* __restrict__ prior) 
   const int64_t o = (int64_t)d * ell.cap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float w = ell.w[o + i];
-    ell.rc[o + i] = make_int2((int)ell.off[o + i], __float_as_int(w * (w * __ldg(prior + ell.src[o + i]))));
+    const int2 e = ell.ent[o + i];
+    ell.rc[o + i] = make_int2(e.x, __float_as_int(w * (w * __ldg(prior + max(e.y, 0)))));      // padding: w = 0
   }
 }
 
 struct EllPlan {
   int64_t cap;
   int ntiles;
-  size_t o_qrow, o_src, o_off, o_w, o_rc, bytes;
+  size_t o_qrow, o_ent, o_w, o_rc, bytes;
 };
 
 EllPlan plan_ell(int64_t Nt, int64_t F) {
@@ -819,8 +851,7 @@ EllPlan plan_ell(int64_t Nt, int64_t F) {
   e.cap = (int64_t)align_up((size_t)(2 * F + 4 * Nt + 64), 64);
   size_t o = 256;
   e.o_qrow = o; o += align_up((size_t)2 * e.ntiles * kQRow * 4, 256);
-  e.o_src = o;  o += align_up((size_t)2 * e.cap * 4, 256);
-  e.o_off = o;  o += align_up((size_t)2 * e.cap * 4, 256);
+  e.o_ent = o;  o += align_up((size_t)2 * e.cap * 8, 256);
   e.o_w = o;    o += align_up((size_t)2 * e.cap * 4, 256);
   e.o_rc = o;   o += align_up((size_t)2 * e.cap * 8, 256);
   e.bytes = o;
@@ -832,8 +863,7 @@ EllView ell_view(void* blob, const EllPlan& e) {
   EllView v{};
   v.counters = reinterpret_cast<int32_t*>(b);
   v.qrow = reinterpret_cast<int32_t*>(b + e.o_qrow);
-  v.src = reinterpret_cast<int32_t*>(b + e.o_src);
-  v.off = reinterpret_cast<uint32_t*>(b + e.o_off);
+  v.ent = reinterpret_cast<int2*>(b + e.o_ent);
   v.w = reinterpret_cast<float*>(b + e.o_w);
   v.rc = reinterpret_cast<int2*>(b + e.o_rc);
   v.cap = e.cap;
@@ -939,6 +969,7 @@ extern "C" int gr_fused_ell_build(const int32_t* rowptr_t, const int32_t* src_t,
     return GR_ERR_WORKSPACE;
   }
   EllView v = ell_view(ell, e);
+  v.weighted = (w_t || w_h) ? 1 : 0;
   GR_CHECK_CUDA(cudaMemsetAsync(v.counters, 0, 256, stream));
   FDir d0{rowptr_t, src_t, rel_t, w_t, nullptr}, d1{rowptr_h, src_h, rel_h, w_h, nullptr};
   fused_ell_build_kernel<<<dim3((unsigned)e.ntiles, 2), BM, 0, stream>>>(d0, d1, v, Nt);
@@ -997,9 +1028,12 @@ extern "C" int gr_fused_layer(const int32_t* rowptr_t, const int32_t* src_t, con
   p.dir[0] = FDir{rowptr_t, src_t, rel_t, w_t, reinterpret_cast<const char*>(pn_fwd)};
   p.dir[1] = FDir{rowptr_h, src_h, rel_h, w_h, reinterpret_cast<const char*>(pn_inv)};
   p.ell = ell_view(ell, ep);
-  // per layer: the entries' coefficients c_f = w (w prior[src]) next to their table offsets, one streaming pass
-  fused_coef_kernel<<<dim3((unsigned)(2 * sm_count()), 2), 256, 0, stream>>>(p.ell, prior);
-  GR_CHECK_LAUNCH();
+  p.ell.weighted = (w_t || w_h) ? 1 : 0;        // must match the build (same graph, same weights)
+  if (p.ell.weighted) {
+    // per layer: the entries' coefficients c_f = w (w prior[src]) next to their table offsets, one streaming pass
+    fused_coef_kernel<<<dim3((unsigned)(2 * sm_count()), 2), 256, 0, stream>>>(p.ell, prior);
+    GR_CHECK_LAUNCH();
+  }
   p.prior = prior; p.ins = ins; p.bias = bias; p.C = C; p.ldc = ldc; p.w_score = w_score; p.dots = dots;
   p.M = (int)M; p.N = (int)N_out; p.n_pad = f.n_pad; p.D = D; p.B = B; p.Nq = N_nodes; p.G = f.G;
   p.ksteps_last = f.ksteps_last; p.num_tiles = (int)ceil_div(M, BM);

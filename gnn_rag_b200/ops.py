@@ -394,7 +394,7 @@ def fused_layer(g, prior, pn_fwd, pn_inv, ins, h_planes, seg_pitch, W, bias, out
                               _p(chi), _p(clo), chi.stride(0) if chi is not None else 0, _p(w_score), _p(dots),
                               B, g.N, D, I, n_out, g.F, flags, _p(ws), ws.numel(), _p(ell), ell.numel(), _stream())
     _lib.check(rc)
-    STATS.launches += 2
+    STATS.launches += 2 if (w_t is not None or w_h is not None) else 1     # weighted graphs: + the coefficient pass
     return out
 
 
