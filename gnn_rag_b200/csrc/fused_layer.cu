@@ -18,8 +18,8 @@
 // tensor core accumulates k-blocks differs (fp32 rounding, ~1e-7).
 //
 // Edge data: once per batch both CSRs are re-laid out slot-major per quad of 4 rows ("quad ELL",
-// fused_ell_build_kernel), once per layer one streaming pass writes {table offset, c_f} per entry (fused_coef_kernel);
-// the kernel's stagers then move a tile's entries into shared memory with ONE bulk copy per direction.  (Staging the
+// fused_ell_build_kernel); the kernel's stagers move a tile's entries into shared memory with ONE bulk copy per
+// direction and turn {table offset, source node} into {table offset, c_f} there (weighted graphs: fused_coef_kernel).  (Staging the
 // CSR slices inside the kernel -- row pointers, src / rel gathers, prior gather, a search for each edge's row -- kept
 // one warp busy for 34 us per tile and bounded the kernel at 400 us; profiles/README.md has the sequence.)
 //
@@ -39,8 +39,7 @@
 // aggregation warp groups (88).  Operand slots are dedicated: slot t < 2I is always written by the aggregation warps,
 // slot 2I always by TMA, so every slot barrier flips once per group and the parity is the group counter.
 //
-// Measured (B200, cfg2: 128 000 rows, D = 200, I = 2): 270 us per layer incl. the 11 us coefficient pass, against 287 us
-// for the unfused pair (125 + 161).  Not faster than that because all three per-SM resources are near their limit at once:
+// Measured (B200, cfg2: 128 000 rows, D = 200, I = 2): 259 us per layer against 287 us for the unfused pair (125 + 161).  Not faster than that because all three per-SM resources are near their limit at once:
 // tensor pipe 115 us of issue (3 products), the L1 / shared-memory SRAM (UMMA operand reads 2.0 MB + TMA writes 1.0 MB
 // + operand stores 0.45 MB + gathers 0.8 MB per tile; l1tex data pipe 68 %, MMA issue slows from 115 to 230 us when the
 // aggregation warps run), and the aggregation's L2 gather latency with only ~28 KB of L1 left beside 226 KB of shared
