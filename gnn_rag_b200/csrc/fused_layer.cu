@@ -648,7 +648,7 @@ fused_layer_kernel(const __grid_constant__ CUtensorMap map_h_hi, const __grid_co
         for (int d = 0; d < 2; ++d) {
           long long t0 = pf.t();
 #pragma unroll
-          for (int j = 0; j < NI; ++j) mbar_wait_sleep(&aempty[d * NI + j], (grp & 1) ^ 1, 20 + d * NI + j, 100);
+          for (int j = 0; j < NI; ++j) mbar_wait_sleep(&aempty[d * NI + j], (grp & 1) ^ 1, 20 + d * NI + j, 0);
           pf.add(0, t0);
           t0 = pf.t();
           if (!(p.debug & 1)) agg_pass<NI>(et, p, d, g, wa, lane, smem_u32(a_slots));
