@@ -65,6 +65,16 @@ def test_new_entry_points_validate_arguments():
     assert lib.gr_pad_table256(None, 0, 1, 8, None, None) == -1
     assert lib.gr_kl_loss_pred(None, None, None, None, None, 1, 1, None) == -1
     assert lib.gr_frontier_rows(None, None, None, None, None, 1, None, None, None) == -1
+    # fused layer kernel: size helpers are pure host arithmetic, null pointers are refused before any CUDA call
+    assert lib.gr_fused_layer_workspace_bytes(200, 208, 2, 200) >= 2 * 200 * 7 * 5 * 32 * 2
+    assert lib.gr_fused_ell_bytes(64, 2000, 512000) > 2 * (2 * 512000 + 4 * 128000) * 8
+    assert lib.gr_fused_ell_bytes(0, 2000, 10) == 0
+    assert lib.gr_fused_ell_build(None, None, None, None, None, None, None, None, 1, 128, 0, None, 0, None) == -1
+    assert lib.gr_fused_layer(None, None, None, None, None, None, None, None, None, None, None, None, None, None, 208,
+                              208, None, 1000, None, None, 0, None, None, 0, None, None, 1, 128, 200, 2, 200, 0, 0,
+                              None, 0, None, 0, None) == -1
+    assert lib.gr_aggregate_backward(None, None, None, None, None, None, None, None, 0, 0, 0, None, None, None, 1, 1, 8,
+                                     1, 0, None) == -1
 
 
 def test_argument_validation_returns_status_codes():
